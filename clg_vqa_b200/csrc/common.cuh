@@ -1,0 +1,117 @@
+// Shared device/host helpers for the clgvqa kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/clgvqa.h"
+
+namespace clg {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// host-side status plumbing
+// ---------------------------------------------------------------------------------------------
+void set_cuda_error(cudaError_t e, const char* where);
+int check_launch(const char* where);   // cudaGetLastError -> status
+
+#define CLG_CUDA_OK(expr, where)                                   \
+  do {                                                             \
+    cudaError_t _e = (expr);                                       \
+    if (_e != cudaSuccess) { clg::set_cuda_error(_e, where); return CLG_ERR_CUDA; } \
+  } while (0)
+
+int num_sms();                 // of the current device (cached)
+int require_sm100();           // CLG_OK or CLG_ERR_ARCH for the current device (cached)
+
+// ---------------------------------------------------------------------------------------------
+// dropout: counter-based hash, shared by all kernels (forward and backward regenerate the mask)
+// ---------------------------------------------------------------------------------------------
+struct Drop {
+  uint32_t thresh;   // keep iff hash >= thresh
+  float scale;       // 1/(1-p)
+  uint64_t seed;
+  uint64_t offset;
+  bool on;
+};
+
+__host__ __device__ inline Drop make_drop(const clgDropout& d) {
+  Drop r;
+  r.on = d.p > 0.f;
+  double t = (double)d.p * 4294967296.0;
+  r.thresh = r.on ? (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t) : 0u;
+  r.scale = r.on ? 1.0f / (1.0f - d.p) : 1.0f;
+  r.seed = d.seed;
+  r.offset = d.offset;
+  return r;
+}
+
+__host__ __device__ __forceinline__ uint32_t mix64to32(uint64_t z) {
+  z ^= z >> 33; z *= 0xff51afd7ed558ccdULL;
+  z ^= z >> 33; z *= 0xc4ceb9fe1a85ec53ULL;
+  z ^= z >> 33;
+  return (uint32_t)z;
+}
+
+// keep-mask for element idx of a site
+__host__ __device__ __forceinline__ bool drop_keep(const Drop& d, uint64_t idx) {
+  uint64_t z = (d.offset + idx) * 0x9E3779B97F4A7C15ULL + d.seed;
+  return mix64to32(z) >= d.thresh;
+}
+
+__host__ __device__ __forceinline__ float drop_apply(const Drop& d, uint64_t idx, float v) {
+  if (!d.on) return v;
+  return drop_keep(d, idx) ? v * d.scale : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float dgelu_erf(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float load_as_f32(const void* p, int dtype, int64_t i) {
+  return dtype == CLG_BF16 ? __bfloat162float(((const bf16*)p)[i]) : ((const float*)p)[i];
+}
+__device__ __forceinline__ void store_from_f32(void* p, int dtype, int64_t i, float v) {
+  if (dtype == CLG_BF16) ((bf16*)p)[i] = __float2bfloat16_rn(v);
+  else ((float*)p)[i] = v;
+}
+
+__host__ __device__ __forceinline__ int64_t map_row(const clgRowMap& m, int64_t r) {
+  if (m.group_rows <= 0) return r;
+  return (r / m.group_rows) * m.group_stride + m.row_offset + (r % m.group_rows);
+}
+
+__device__ __forceinline__ bool mask_bit(const uint32_t* bits, int64_t i) {
+  return (bits[i >> 5] >> (i & 31)) & 1u;
+}
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace clg

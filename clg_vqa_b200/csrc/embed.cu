@@ -1,0 +1,87 @@
+// Text-embedding gather (word + position + token-type rows, fp32 tables) and its scatter-add
+// backward.  One warp per token; rows are 768 floats = 3 KB, read / written as float4 (coalesced).
+// Position ids follow create_position_ids_from_input_ids (embeddings.py:L157-170):
+//   pos = cumsum(ids != pad)[t] * (ids[t] != pad) + pad       (computed per sample with a warp scan)
+#include "common.cuh"
+
+namespace clg {
+
+static constexpr int EMB_WARPS = 8;
+
+__device__ __forceinline__ int text_pos_id(const int64_t* ids_row, int t, int T, int pad_id, int lane) {
+  // inclusive count of non-pad tokens in [0, t]; T <= 64 handled with two ballots
+  int cnt = 0;
+  for (int base = 0; base <= t; base += 32) {
+    const int idx = base + lane;
+    const bool nz = (idx < T) && (idx <= t) && (ids_row[idx] != pad_id);
+    cnt += __popc(__ballot_sync(0xffffffffu, nz));
+  }
+  const bool self = ids_row[t] != pad_id;
+  return (self ? cnt : 0) + pad_id;
+}
+
+__global__ void __launch_bounds__(EMB_WARPS * 32)
+embed_text_fwd_kernel(const clgEmbedTextParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tok = (int64_t)blockIdx.x * EMB_WARPS + (threadIdx.x >> 5);
+  if (tok >= (int64_t)p.B * p.T) return;
+  const int b = (int)(tok / p.T), t = (int)(tok % p.T);
+  const int64_t id = p.ids[tok];
+  int pos;
+  if (p.pos_mode == 0) pos = text_pos_id(p.ids + (int64_t)b * p.T, t, p.T, p.pad_id, lane);
+  else pos = p.pos_base + t;
+  const float* w = p.word + id * p.N;
+  const float* pe = p.pos ? p.pos + (int64_t)pos * p.N : nullptr;
+  const float* te = (p.type && p.seg) ? p.type + p.seg[tok] * p.N : nullptr;
+  float* o = p.out + map_row(p.out_map, tok) * p.ld_out;
+  for (int c = lane * 4; c < p.N; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(w + c);
+    if (pe) { const float4 a = *reinterpret_cast<const float4*>(pe + c); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+    if (te) { const float4 a = *reinterpret_cast<const float4*>(te + c); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+    *reinterpret_cast<float4*>(o + c) = v;
+  }
+}
+
+__global__ void __launch_bounds__(EMB_WARPS * 32)
+embed_text_bwd_kernel(const clgEmbedTextBwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tok = (int64_t)blockIdx.x * EMB_WARPS + (threadIdx.x >> 5);
+  if (tok >= (int64_t)p.B * p.T) return;
+  const int b = (int)(tok / p.T), t = (int)(tok % p.T);
+  const int64_t id = p.ids[tok];
+  int pos;
+  if (p.pos_mode == 0) pos = text_pos_id(p.ids + (int64_t)b * p.T, t, p.T, p.pad_id, lane);
+  else pos = p.pos_base + t;
+  const float* g = p.dout + map_row(p.dout_map, tok) * p.ld_dout;
+  float* dw = (p.dword && id != p.pad_id) ? p.dword + id * p.N : nullptr;   // padding_idx row gets no gradient
+  float* dp = p.dpos ? p.dpos + (int64_t)pos * p.N : nullptr;
+  float* dt = (p.dtype_tab && p.seg) ? p.dtype_tab + p.seg[tok] * p.N : nullptr;
+  for (int c = lane; c < p.N; c += 32) {
+    const float v = g[c];
+    if (dw) atomicAdd(dw + c, v);
+    if (dp) atomicAdd(dp + c, v);
+    if (dt) atomicAdd(dt + c, v);
+  }
+}
+
+}  // namespace clg
+
+extern "C" int clg_embed_text_fwd(const clgEmbedTextParams* p, clgStream_t stream) {
+  using namespace clg;
+  if (!p || !p->ids || !p->word || !p->out || p->B <= 0 || p->T <= 0 || (p->N & 3) || p->T > 64 * 32) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  const int64_t toks = (int64_t)p->B * p->T;
+  embed_text_fwd_kernel<<<(unsigned)ceil_div64(toks, EMB_WARPS), EMB_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(*p);
+  return check_launch("embed_text_fwd_kernel");
+}
+
+extern "C" int clg_embed_text_bwd(const clgEmbedTextBwdParams* p, clgStream_t stream) {
+  using namespace clg;
+  if (!p || !p->ids || !p->dout || p->B <= 0 || p->T <= 0) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  const int64_t toks = (int64_t)p->B * p->T;
+  embed_text_bwd_kernel<<<(unsigned)ceil_div64(toks, EMB_WARPS), EMB_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(*p);
+  return check_launch("embed_text_bwd_kernel");
+}

@@ -1,0 +1,83 @@
+// fp32-FFMA GEMM: the fp32 correctness mode and the small / oddly shaped GEMMs of the head
+// (pooler, classifier, K = 7 location projection).  Operands may be fp32 or bf16 (converted exactly
+// to fp32 on load), any major-ness, any leading dimension.  Shares the epilogue with gemm_tc.cu.
+#include "gemm_epilogue.cuh"
+
+namespace clg {
+
+static constexpr int SBM = 64, SBN = 128, SBK = 16;
+
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const TA* __restrict__ A, const TB* __restrict__ B, int M, int N, int K, int64_t lda, int64_t ldb,
+                 int a_k, int b_k, const EpiArgs e) {
+  __shared__ float As[SBK][SBM + 4];
+  __shared__ float Bs[SBK][SBN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += SBK) {
+    // A tile: 64 x 16
+#pragma unroll
+    for (int it = 0; it < (SBM * SBK) / 256; ++it) {
+      const int i = tid + it * 256;
+      int m, k;
+      if (a_k) { k = i % SBK; m = i / SBK; } else { m = i % SBM; k = i / SBM; }
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < K) v = to_f32<TA>(a_k ? A[(int64_t)gm * lda + gk] : A[(int64_t)gk * lda + gm]);
+      As[k][m] = v;
+    }
+#pragma unroll
+    for (int it = 0; it < (SBN * SBK) / 256; ++it) {
+      const int i = tid + it * 256;
+      int n, k;
+      if (b_k) { k = i % SBK; n = i / SBK; } else { n = i % SBN; k = i / SBN; }
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < K) v = to_f32<TB>(b_k ? B[(int64_t)gn * ldb + gk] : B[(int64_t)gk * ldb + gn]);
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SBK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][tx * 8 + 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) epi_row_chunk<8>(e, m0 + ty * 4 + i, n0 + tx * 8, acc[i]);
+}
+
+template <typename TA, typename TB>
+static int launch_simt(const clgGemmParams& p, cudaStream_t s) {
+  const EpiArgs e = make_epi(p);
+  dim3 grid((p.N + SBN - 1) / SBN, (p.M + SBM - 1) / SBM);
+  gemm_simt_kernel<TA, TB><<<grid, 256, 0, s>>>((const TA*)p.A, (const TB*)p.B, p.M, p.N, p.K, p.lda, p.ldb,
+                                                p.a_kmajor, p.b_kmajor, e);
+  return check_launch("gemm_simt_kernel");
+}
+
+int gemm_simt(const clgGemmParams& p, cudaStream_t s) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return CLG_ERR_ARG;
+  if (p.a_dtype == CLG_F32 && p.b_dtype == CLG_F32) return launch_simt<float, float>(p, s);
+  if (p.a_dtype == CLG_BF16 && p.b_dtype == CLG_BF16) return launch_simt<bf16, bf16>(p, s);
+  if (p.a_dtype == CLG_BF16 && p.b_dtype == CLG_F32) return launch_simt<bf16, float>(p, s);
+  return launch_simt<float, bf16>(p, s);
+}
+
+}  // namespace clg

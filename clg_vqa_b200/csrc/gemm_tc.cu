@@ -1,0 +1,385 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = epi( A(m,k) * B(n,k) ), bf16 operands,
+// fp32 accumulation in tensor memory.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane issues
+// tcgen05.mma; the warp also owns the TMEM allocation), warps 2-5 = epilogue (tcgen05.ld -> registers
+// -> fused epilogue -> global).  Two accumulator stages in TMEM (2 x BN columns) let the epilogue of
+// tile i overlap the MMAs of tile i+1; a KSTAGES-deep smem ring (128B-swizzled TMA boxes) feeds the
+// tensor core.  Both operands may be K-major (forward / dgrad through a transposed copy) or MN-major
+// (dgrad on W[N,K] as stored, wgrad on dY / X as stored) - selected by the UMMA descriptors, no
+// transposes in memory.  Optional split-K (atomic fp32 accumulate) for the wgrad shapes whose output
+// has too few tiles to fill 148 SMs.
+#include <cuda.h>
+#include <mutex>
+#include "gemm_epilogue.cuh"
+
+namespace clg {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
+static constexpr int UMMA_K = 16;
+static constexpr int NUM_THREADS = 192;  // 6 warps
+static constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KiB
+
+template <int BN> struct TileCfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int KSTAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;          // power of two >= 32 for BN in {64,128,256}
+  static constexpr int SMEM_BYTES = KSTAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (sm_100): start address, leading / stride byte offsets (>>4),
+// version = 1 (bits 46-47), layout = SWIZZLE_128B (2) in bits 61-63.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor for kind::f16: D = F32 (bit 4), A = B = BF16 (bits 7, 10),
+// a_major (bit 15) / b_major (bit 16): 0 = K-major, 1 = MN-major; N>>3 at bits 17-22; M>>4 at 24-28.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct TcArgs {
+  int M, N, K;
+  int num_m, num_n, splits, kper, kblocks;
+};
+
+template <int BN, bool A_K, bool B_K>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const TcArgs t, const EpiArgs e) {
+  using Cfg = TileCfg<BN>;
+  constexpr int KSTAGES = Cfg::KSTAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + KSTAGES * Cfg::STAGE_BYTES;
+  // barrier layout (8 B each): full[KSTAGES], empty[KSTAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (KSTAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * KSTAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * KSTAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * KSTAGES + 4);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + KSTAGES * Cfg::STAGE_BYTES + 8 * (2 * KSTAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    for (int s = 0; s < KSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int total_work = t.num_m * t.num_n * t.splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % t.splits;
+        const int tile = w / t.splits;
+        const int n_blk = tile % t.num_n, m_blk = tile / t.num_n;
+        const int kb0 = split * t.kper;
+        const int kb1 = min(t.kblocks, kb0 + t.kper);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + A_TILE_BYTES;
+          if (A_K) {
+            tma_load_2d(sa, &tma_a, full_bar(stage), kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sa + j * (64 * BK * 2), &tma_a, full_bar(stage), m_blk * BM + j * 64, kb * BK);
+          }
+          if (B_K) {
+            tma_load_2d(sb, &tma_b, full_bar(stage), kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * (64 * BK * 2), &tma_b, full_bar(stage), n_blk * BN + j * 64, kb * BK);
+          }
+          if (++stage == KSTAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, !A_K, !B_K);
+      int stage = 0; uint32_t phase = 0;
+      int local = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++local) {
+        const int split = w % t.splits;
+        const int kb0 = split * t.kper;
+        const int kb1 = min(t.kblocks, kb0 + t.kper);
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: 8-row groups 1024 B apart (SBO), advance 32 B per UMMA_K inside the swizzle row.
+            // MN-major: 64-wide MN blocks 8192 B apart (LBO), 8-k groups 1024 B apart (SBO),
+            //           advance 16 k-rows = 2048 B per UMMA_K.
+            const uint64_t adesc = A_K ? umma_desc(sa + k * (UMMA_K * 2), 16, 1024)
+                                       : umma_desc(sa + k * (UMMA_K * 128), 64 * BK * 2, 1024);
+            const uint64_t bdesc = B_K ? umma_desc(sb + k * (UMMA_K * 2), 16, 1024)
+                                       : umma_desc(sb + k * (UMMA_K * 128), 64 * BK * 2, 1024);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
+          if (++stage == KSTAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(as));        // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    const int q = warp & 3;                // TMEM lane quarter this warp may access
+    int local = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++local) {
+      const int tile = w / t.splits;
+      const int n_blk = tile % t.num_n, m_blk = tile / t.num_n;
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(tfull_bar(as), aphase);
+      tcgen05_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)(c * 32), v);
+        epi_row_chunk<32>(e, row, n_blk * BN + c * 32, v);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor [outer, inner] with row pitch ld elements; box = 64 x box_outer, 128B swizzle.
+static int make_tmap(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return CLG_ERR_CUDA;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return CLG_ERR_UNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld * 2)};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled"); return CLG_ERR_CUDA; }
+  return CLG_OK;
+}
+
+template <int BN, bool A_K, bool B_K>
+static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t stream) {
+  using Cfg = TileCfg<BN>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, A_K, B_K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::SMEM_BYTES);
+  });
+  CLG_CUDA_OK(attr_err, "cudaFuncSetAttribute(gemm_tc)");
+
+  CUtensorMap ta, tb;
+  int st;
+  if (A_K) st = make_tmap(&ta, p.A, p.K, p.M, p.lda, BM);
+  else     st = make_tmap(&ta, p.A, p.M, p.K, p.lda, BK);
+  if (st != CLG_OK) return st;
+  if (B_K) st = make_tmap(&tb, p.B, p.K, p.N, p.ldb, BN);
+  else     st = make_tmap(&tb, p.B, p.N, p.K, p.ldb, BK);
+  if (st != CLG_OK) return st;
+
+  TcArgs t;
+  t.M = p.M; t.N = p.N; t.K = p.K;
+  t.num_m = (p.M + BM - 1) / BM;
+  t.num_n = (p.N + BN - 1) / BN;
+  t.kblocks = (p.K + BK - 1) / BK;
+  const int sms = num_sms();
+  int splits = p.split_k;
+  const bool can_split = (p.act == CLG_ACT_NONE && p.bias == nullptr && p.residual == nullptr &&
+                          p.c_dtype == CLG_F32 && !p.dropout.p);
+  if (splits <= 0) {
+    splits = 1;
+    const int tiles = t.num_m * t.num_n;
+    if (can_split && tiles < sms && t.kblocks >= 16) {
+      // pick the split count that best fills whole waves of SMs, >= 8 k-blocks (K = 512) per split
+      const int max_s = t.kblocks / 8 < 32 ? t.kblocks / 8 : 32;
+      double best = (double)tiles / sms;
+      for (int s = 2; s <= max_s; ++s) {
+        const int tot = tiles * s;
+        const int waves = (tot + sms - 1) / sms;
+        const double ef = (double)tot / ((double)waves * sms);
+        if (ef > best + 0.02) { best = ef; splits = s; }
+      }
+    }
+  }
+  if (splits > 1 && !can_split) return CLG_ERR_ARG;
+  t.kper = (t.kblocks + splits - 1) / splits;
+  t.splits = (t.kblocks + t.kper - 1) / t.kper;
+  EpiArgs e = e0;
+  if (t.splits > 1) {
+    if (!p.accumulate) {
+      // split-K accumulates atomically: C must start from zero
+      CLG_CUDA_OK(cudaMemset2DAsync(p.C, p.ldc * sizeof(float), 0, (size_t)p.N * sizeof(float), p.M, stream),
+                  "memset(split-K C)");
+    }
+    e.accumulate = 2;
+  }
+  const int total = t.num_m * t.num_n * t.splits;
+  const int grid = total < sms ? total : sms;
+  gemm_tc_kernel<BN, A_K, B_K><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, t, e);
+  return check_launch("gemm_tc_kernel");
+}
+
+template <int BN>
+static int dispatch_major(const clgGemmParams& p, const EpiArgs& e, cudaStream_t s) {
+  if (p.a_kmajor && p.b_kmajor) return launch_tc<BN, true, true>(p, e, s);
+  if (p.a_kmajor && !p.b_kmajor) return launch_tc<BN, true, false>(p, e, s);
+  if (!p.a_kmajor && !p.b_kmajor) return launch_tc<BN, false, false>(p, e, s);
+  return launch_tc<BN, false, true>(p, e, s);
+}
+
+// entry used by clg_gemm
+int gemm_tc(const clgGemmParams& p, cudaStream_t stream) {
+  if (p.a_dtype != CLG_BF16 || p.b_dtype != CLG_BF16) return CLG_ERR_UNSUPPORTED;
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return CLG_ERR_ARG;
+  const EpiArgs e = make_epi(p);
+  // Tile choice: BN = 256 when the tile count still fills the machine in whole waves reasonably,
+  // BN = 128 for the N = 768 family (fewer idle SMs in the last wave).
+  const int sms = num_sms();
+  const int num_m = (p.M + BM - 1) / BM;
+  auto eff = [&](int bn) {
+    const int tiles = num_m * ((p.N + bn - 1) / bn);
+    const int waves = (tiles + sms - 1) / sms;
+    return (double)tiles / ((double)waves * sms);
+  };
+  int bn = 256;
+  if (p.N <= 64) bn = 64;
+  else if (p.N <= 128) bn = 128;
+  else if (eff(128) > eff(256) + 0.08) bn = 128;
+  if (bn == 256) return dispatch_major<256>(p, e, stream);
+  if (bn == 128) return dispatch_major<128>(p, e, stream);
+  return dispatch_major<64>(p, e, stream);
+}
+
+}  // namespace clg

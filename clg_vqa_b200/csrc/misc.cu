@@ -1,0 +1,171 @@
+// Small HBM-bound utilities: dtype cast, mask packing / application, column sums, key-bias
+// construction from the int64 masks of the module interface, in-place dropout.
+#include "common.cuh"
+
+namespace clg {
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
+  const int64_t n8 = n >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+    reinterpret_cast<uint4*>(dst)[i] = u;
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (n8 << 3) + threadIdx.x; i < n; i += blockDim.x) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+__global__ void pack_mask_kernel(const float* __restrict__ mask, uint32_t* __restrict__ bits, int64_t n) {
+  // one warp packs 32 consecutive elements into one word with a ballot
+  const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwords = (n + 31) >> 5;
+  for (int64_t w = gwarp; w < nwords; w += nwarps) {
+    const int64_t i = w * 32 + lane;
+    const bool on = (i < n) && (mask[i] != 0.f);
+    const uint32_t b = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) bits[w] = b;
+  }
+}
+
+__global__ void apply_mask_kernel(float* __restrict__ w, const uint32_t* __restrict__ bits, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    w[i] *= mask_bit(bits, i) ? 1.f : 0.f;
+}
+
+// out[n] += sum_m X[m, n]; block = 32 x 8 threads, each block owns 32 columns and a slab of rows
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, int M, int N, float* __restrict__ out, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float acc = 0.f;
+  if (col < N)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += to_f32<T>(x[(int64_t)r * ld + col]);
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x];
+    atomicAdd(out + col, s);
+  }
+}
+
+__global__ void key_bias_kernel(const int64_t* __restrict__ txt_mask, const int64_t* __restrict__ img_mask, int B, int T,
+                                int R, int m3p_prefix, float* __restrict__ key_bias, uint8_t* __restrict__ row_valid) {
+  const int S = T + R;
+  const int b = blockIdx.x;
+  if (!m3p_prefix) {
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+      const int64_t m = s < T ? txt_mask[(int64_t)b * T + s] : img_mask[(int64_t)b * R + (s - T)];
+      // (1 - mask) * -10000 with the mask cast to the parameter dtype (encoders.py:L985-995)
+      key_bias[(int64_t)b * S + s] = (1.0f - (float)m) * -10000.0f;
+      if (row_valid) row_valid[(int64_t)b * S + s] = 1;
+    }
+  } else {
+    __shared__ int n_valid;
+    if (threadIdx.x == 0) n_valid = 0;
+    __syncthreads();
+    int loc = 0;
+    for (int s = threadIdx.x; s < T; s += blockDim.x) loc += (int)txt_mask[(int64_t)b * T + s];
+    for (int s = threadIdx.x; s < R; s += blockDim.x) loc += (int)img_mask[(int64_t)b * R + s];
+    atomicAdd(&n_valid, loc);
+    __syncthreads();
+    const int n = n_valid;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+      const bool v = s < n;
+      key_bias[(int64_t)b * S + s] = v ? 0.f : -INFINITY;
+      if (row_valid) row_valid[(int64_t)b * S + s] = v ? 1 : 0;
+    }
+  }
+}
+
+__global__ void dropout_inplace_kernel(float* __restrict__ x, int64_t n, const Drop d) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = drop_apply(d, (uint64_t)i, x[i]);
+}
+
+static int ew_grid(int64_t work_items, int threads) {
+  int64_t g = (work_items + threads - 1) / threads;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace clg
+
+extern "C" int clg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, clgStream_t stream) {
+  using namespace clg;
+  if (!src || !dst || n < 0) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  if (n == 0) return CLG_OK;
+  cast_f32_bf16_kernel<<<ew_grid(n / 8 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, (bf16*)dst, n);
+  return check_launch("cast_f32_bf16_kernel");
+}
+
+extern "C" int clg_pack_mask(const float* mask, uint32_t* bits, int64_t n, clgStream_t stream) {
+  using namespace clg;
+  if (!mask || !bits || n < 0) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  if (n == 0) return CLG_OK;
+  pack_mask_kernel<<<ew_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, bits, n);
+  return check_launch("pack_mask_kernel");
+}
+
+extern "C" int clg_apply_mask(float* w, const uint32_t* bits, int64_t n, clgStream_t stream) {
+  using namespace clg;
+  if (!w || !bits || n < 0) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  if (n == 0) return CLG_OK;
+  apply_mask_kernel<<<ew_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, bits, n);
+  return check_launch("apply_mask_kernel");
+}
+
+extern "C" int clg_colsum(const void* x, int32_t dtype, int64_t ld, int32_t M, int32_t N, float* out, clgStream_t stream) {
+  using namespace clg;
+  if (!x || !out || M <= 0 || N <= 0) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  const int col_blocks = (N + 31) / 32;
+  int row_blocks = (num_sms() * 4 + col_blocks - 1) / col_blocks;
+  if (row_blocks > (M + 63) / 64) row_blocks = (M + 63) / 64;
+  if (row_blocks < 1) row_blocks = 1;
+  const int rows_per_block = (M + row_blocks - 1) / row_blocks;
+  dim3 grid(col_blocks, row_blocks), block(32, 8);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CLG_BF16) colsum_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, ld, M, N, out, rows_per_block);
+  else colsum_kernel<float><<<grid, block, 0, s>>>((const float*)x, ld, M, N, out, rows_per_block);
+  return check_launch("colsum_kernel");
+}
+
+extern "C" int clg_build_key_bias(const int64_t* txt_mask, const int64_t* img_mask, int32_t B, int32_t T, int32_t R,
+                                  int32_t m3p_prefix, float* key_bias, uint8_t* row_valid, clgStream_t stream) {
+  using namespace clg;
+  if (!txt_mask || !img_mask || !key_bias || B <= 0 || T < 0 || R < 0) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  key_bias_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(txt_mask, img_mask, B, T, R, m3p_prefix, key_bias, row_valid);
+  return check_launch("key_bias_kernel");
+}
+
+extern "C" int clg_dropout_inplace(float* x, int64_t n, const clgDropout* d, clgStream_t stream) {
+  using namespace clg;
+  if (!x || !d || n < 0) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  if (n == 0 || d->p <= 0.f) return CLG_OK;
+  dropout_inplace_kernel<<<ew_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, make_drop(*d));
+  return check_launch("dropout_inplace_kernel");
+}

@@ -1,0 +1,170 @@
+// Optimiser step over flat fp32 arenas: global gradient norm (two deterministic passes), then one
+// multi-tensor kernel doing clip-scale + pytorch-transformers AdamW +
+// decoupled decay, and refreshing the masked bf16 shadow copy the GEMMs read (W_eff = W (.) M, the
+// torch.nn.utils.prune re-parametrisation of train_task_sft.py:L461 folded into the update).
+// HBM-bound: 7 fp32 accesses per parameter (read p, g, m, v; write p, m, v) + 2 B shadow write.
+#include <string.h>
+#include "common.cuh"
+
+namespace clg {
+
+static constexpr int CHUNK = 2048;
+static constexpr int OPT_THREADS = 256;   // 8 elements per thread per chunk
+
+__global__ void __launch_bounds__(256)
+sumsq_partial_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partials) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  const int64_t n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(g4 + i);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) acc += g[i] * g[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    partials[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_final_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
+  __shared__ double sh[256];
+  double a = 0;
+  for (int i = threadIdx.x; i < n; i += 256) a += (double)partials[i];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] += (float)sh[0];
+}
+
+template <bool UPDATE>
+__global__ void __launch_bounds__(OPT_THREADS)
+adamw_kernel(const clgAdamWParams p) {
+  const int64_t nchunks = p.n / CHUNK;
+  float coef = p.gscale;
+  if (UPDATE && p.sumsq) {
+    const float total = sqrtf(p.sumsq[0]) * p.gscale;
+    const float c = p.max_norm / (total + 1e-6f);
+    if (c < 1.f) coef *= c;
+  }
+  for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int t = p.chunk_tensor[c];
+    if (t < 0) continue;
+    const clgTensorMeta tm = p.tensors[t];
+    const int64_t base = c * CHUNK + (int64_t)threadIdx.x * 8;
+    const int64_t rel = base - tm.start;          // element offset inside the tensor
+    if (rel >= tm.numel) continue;                // tail padding of the tensor's last chunk
+    float pv[8];
+    {
+      const float4 a = *reinterpret_cast<const float4*>(p.p + base);
+      const float4 b = *reinterpret_cast<const float4*>(p.p + base + 4);
+      pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w; pv[4] = b.x; pv[5] = b.y; pv[6] = b.z; pv[7] = b.w;
+    }
+    if (UPDATE) {
+      float gv[8], mv[8], vv[8];
+      {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.g + base));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.g + base + 4));
+        gv[0] = a.x; gv[1] = a.y; gv[2] = a.z; gv[3] = a.w; gv[4] = b.x; gv[5] = b.y; gv[6] = b.z; gv[7] = b.w;
+        const float4 c0 = *reinterpret_cast<const float4*>(p.m + base);
+        const float4 c1 = *reinterpret_cast<const float4*>(p.m + base + 4);
+        mv[0] = c0.x; mv[1] = c0.y; mv[2] = c0.z; mv[3] = c0.w; mv[4] = c1.x; mv[5] = c1.y; mv[6] = c1.z; mv[7] = c1.w;
+        const float4 d0 = *reinterpret_cast<const float4*>(p.v + base);
+        const float4 d1 = *reinterpret_cast<const float4*>(p.v + base + 4);
+        vv[0] = d0.x; vv[1] = d0.y; vv[2] = d0.z; vv[3] = d0.w; vv[4] = d1.x; vv[5] = d1.y; vv[6] = d1.z; vv[7] = d1.w;
+      }
+      const float step_size = tm.lr * sqrtf(p.bias_c2) / p.bias_c1;
+      const float decay = tm.lr * tm.wd;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = gv[j] * coef;
+        mv[j] = mv[j] * p.beta1 + (1.f - p.beta1) * g;
+        vv[j] = vv[j] * p.beta2 + (1.f - p.beta2) * g * g;
+        const float denom = sqrtf(vv[j]) + p.eps;
+        float w = pv[j] - step_size * (mv[j] / denom);
+        if (tm.wd > 0.f) w = w - decay * w;
+        pv[j] = w;
+      }
+      *reinterpret_cast<float4*>(p.p + base) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+      *reinterpret_cast<float4*>(p.p + base + 4) = make_float4(pv[4], pv[5], pv[6], pv[7]);
+      *reinterpret_cast<float4*>(p.m + base) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+      *reinterpret_cast<float4*>(p.m + base + 4) = make_float4(mv[4], mv[5], mv[6], mv[7]);
+      *reinterpret_cast<float4*>(p.v + base) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      *reinterpret_cast<float4*>(p.v + base + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
+    }
+    if (p.shadow && tm.shadow_off >= 0) {
+      if (tm.mask_off >= 0) {
+        // 8 consecutive mask bits; rel is a multiple of 8 and mask_off a multiple of 32
+        const int64_t bit0 = tm.mask_off + rel;
+        const uint32_t bits = (p.mask_bits[bit0 >> 5] >> (bit0 & 31)) & 0xffu;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pv[j] *= ((bits >> j) & 1u) ? 1.f : 0.f;
+      }
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(pv[0], pv[1]);
+      __nv_bfloat162 h1 = __floats2bfloat162_rn(pv[2], pv[3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[4], pv[5]);
+      __nv_bfloat162 h3 = __floats2bfloat162_rn(pv[6], pv[7]);
+      uint4 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+      u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>((bf16*)p.shadow + tm.shadow_off + rel) = u;
+    }
+  }
+}
+
+}  // namespace clg
+
+extern "C" int clg_sumsq(const float* g, int64_t n, float* partials, int32_t num_partials, float* out, clgStream_t stream) {
+  using namespace clg;
+  if (!g || !partials || !out || n < 0 || num_partials <= 0) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int grid = num_sms() * 4;
+  if (grid > num_partials) grid = num_partials;
+  sumsq_partial_kernel<<<grid, 256, 0, s>>>(g, n, partials);
+  st = check_launch("sumsq_partial_kernel");
+  if (st != CLG_OK) return st;
+  sumsq_final_kernel<<<1, 256, 0, s>>>(partials, grid, out);
+  return check_launch("sumsq_final_kernel");
+}
+
+extern "C" int clg_adamw_step(const clgAdamWParams* p, clgStream_t stream) {
+  using namespace clg;
+  if (!p || !p->p || !p->g || !p->m || !p->v || !p->chunk_tensor || !p->tensors || p->n <= 0 || (p->n % CHUNK)) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  const int64_t nchunks = p->n / CHUNK;
+  int64_t grid = (int64_t)num_sms() * 16;
+  if (grid > nchunks) grid = nchunks;
+  adamw_kernel<true><<<(unsigned)grid, OPT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*p);
+  return check_launch("adamw_kernel");
+}
+
+extern "C" int clg_cast_shadow(const float* params, int64_t n, const int32_t* chunk_tensor, const clgTensorMeta* tensors,
+                               void* shadow, const uint32_t* mask_bits, clgStream_t stream) {
+  using namespace clg;
+  if (!params || !chunk_tensor || !tensors || !shadow || n <= 0 || (n % CHUNK)) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  clgAdamWParams p;
+  memset(&p, 0, sizeof(p));
+  p.p = const_cast<float*>(params);
+  p.n = n; p.chunk_tensor = chunk_tensor; p.tensors = tensors; p.shadow = shadow; p.mask_bits = mask_bits;
+  p.gscale = 1.f;
+  const int64_t nchunks = n / CHUNK;
+  int64_t grid = (int64_t)num_sms() * 16;
+  if (grid > nchunks) grid = nchunks;
+  adamw_kernel<false><<<(unsigned)grid, OPT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("cast_shadow_kernel");
+}
