@@ -1,0 +1,315 @@
+"""Thin torch-tensor wrappers over the C ABI (include/clgvqa.h).  Device memory, streams and
+dtype bookkeeping only; every arithmetic step happens in libclgvqa.so.  All functions enqueue on
+torch's current CUDA stream and raise `ClgError` on any failure (no fallback)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from ._lib import (ACT_DGELU, ACT_DRELU, ACT_DTANH, ACT_GELU, ACT_NONE, ACT_RELU, ACT_TANH,  # noqa: F401
+                   CLG_BF16, CLG_F32, GEMM_AUTO, GEMM_SIMT, GEMM_TC, ClgError)
+
+_launches = 0   # number of C-ABI kernel entry calls (bench.py reports it as gpu_launches)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return CLG_F32
+    if t.dtype == torch.bfloat16:
+        return CLG_BF16
+    raise ClgError("unsupported dtype %s" % t.dtype)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise ClgError("clg_vqa_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU path" % t.device)
+
+
+class DropSite:
+    """(p, seed, offset) of one dropout site; p = 0 disables."""
+    __slots__ = ("p", "seed", "offset")
+
+    def __init__(self, p: float = 0.0, seed: int = 0, offset: int = 0):
+        self.p, self.seed, self.offset = float(p), int(seed), int(offset)
+
+    def c(self) -> L.Dropout:
+        return L.Dropout(self.p, 0, self.seed & 0xFFFFFFFFFFFFFFFF, self.offset & 0xFFFFFFFFFFFFFFFF)
+
+
+NO_DROP = DropSite()
+
+
+def rowmap(group_rows=0, row_offset=0, group_stride=0) -> L.RowMap:
+    return L.RowMap(int(group_rows), int(row_offset), int(group_stride))
+
+
+def _ld(t: torch.Tensor) -> int:
+    """leading dimension (row pitch in elements) of a 2-D row-major view"""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ClgError("expected a 2-D tensor with unit inner stride, got shape %s stride %s" % (tuple(t.shape), t.stride()))
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def gemm(a, b, c, *, a_kmajor=True, b_kmajor=True, M=None, N=None, K=None, alpha=1.0, act=ACT_NONE, bias=None,
+         residual=None, aux_in=None, aux_out=None, mask_bits=None, accumulate=False, dropout: DropSite = NO_DROP,
+         drop_before_act=False, backend=GEMM_AUTO, split_k=0):
+    """C[M,N] = epi(alpha * A(m,k) B(n,k)).  a: [M,K] if a_kmajor else [K,M]; b: [N,K] if b_kmajor else [K,N]."""
+    _need_cuda(a, b, c)
+    if M is None:
+        M = a.shape[0] if a_kmajor else a.shape[1]
+    if K is None:
+        K = a.shape[1] if a_kmajor else a.shape[0]
+    if N is None:
+        N = b.shape[0] if b_kmajor else b.shape[1]
+    p = L.GemmParams()
+    p.A, p.B, p.C = a.data_ptr(), b.data_ptr(), c.data_ptr()
+    p.a_dtype, p.b_dtype, p.c_dtype = _dt(a), _dt(b), _dt(c)
+    p.M, p.N, p.K = int(M), int(N), int(K)
+    p.lda, p.ldb, p.ldc = _ld(a), _ld(b), _ld(c)
+    p.a_kmajor, p.b_kmajor = int(a_kmajor), int(b_kmajor)
+    p.alpha, p.act = float(alpha), int(act)
+    p.bias = _ptr(bias)
+    if residual is not None:
+        p.residual, p.ld_res = residual.data_ptr(), _ld(residual)
+    if aux_in is not None:
+        p.aux_in, p.ld_aux_in, p.aux_in_dtype = aux_in.data_ptr(), _ld(aux_in), _dt(aux_in)
+    if aux_out is not None:
+        p.aux_out, p.ld_aux_out, p.aux_out_dtype = aux_out.data_ptr(), _ld(aux_out), _dt(aux_out)
+    p.mask_bits = _ptr(mask_bits)
+    p.accumulate = int(bool(accumulate))
+    p.drop_before_act = int(bool(drop_before_act))
+    p.dropout = dropout.c()
+    p.backend, p.split_k = int(backend), int(split_k)
+    L.check(L.load().clg_gemm(C.byref(p), _stream()), "clg_gemm")
+    _count()
+    return c
+
+
+def layernorm_fwd(x, gamma, beta, eps, *, y=None, y_lowp=None, mean=None, rstd=None, rows=None, out_map=None,
+                  add_mat=None, add_map=None, add_vec=None, row_valid=None, valid_pre=False, valid_post=False,
+                  dropout: DropSite = NO_DROP):
+    _need_cuda(x, gamma, beta)
+    p = L.LayerNormFwdParams()
+    p.x, p.ldx = x.data_ptr(), _ld(x)
+    p.gamma, p.beta = gamma.data_ptr(), beta.data_ptr()
+    if y is not None:
+        p.y, p.ldy = y.data_ptr(), _ld(y)
+    if y_lowp is not None:
+        p.y_lowp, p.ldy_lowp, p.lowp_dtype = y_lowp.data_ptr(), _ld(y_lowp), _dt(y_lowp)
+    p.mean, p.rstd = _ptr(mean), _ptr(rstd)
+    p.rows = int(x.shape[0] if rows is None else rows)
+    p.N = int(x.shape[1])
+    p.eps = float(eps)
+    if out_map is not None:
+        p.out_map = out_map
+    if add_mat is not None:
+        p.add_mat, p.ld_add = add_mat.data_ptr(), _ld(add_mat)
+        if add_map is not None:
+            p.add_map = add_map
+    p.add_vec = _ptr(add_vec)
+    p.row_valid = _ptr(row_valid)
+    p.valid_pre, p.valid_post = int(valid_pre), int(valid_post)
+    p.dropout = dropout.c()
+    L.check(L.load().clg_layernorm_fwd(C.byref(p), _stream()), "clg_layernorm_fwd")
+    _count()
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx=None, dx_lowp=None, dgamma=None, dbeta=None, dbias=None,
+                  rows=None, dy_map=None, row_valid=None, valid_pre=False, valid_post=False,
+                  dropout_out: DropSite = NO_DROP, dropout_in: DropSite = NO_DROP):
+    _need_cuda(dy, x, gamma)
+    p = L.LayerNormBwdParams()
+    p.dy, p.lddy = dy.data_ptr(), _ld(dy)
+    if dy_map is not None:
+        p.dy_map = dy_map
+    p.x, p.ldx = x.data_ptr(), _ld(x)
+    p.gamma, p.mean, p.rstd = gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    if dx is not None:
+        p.dx, p.lddx = dx.data_ptr(), _ld(dx)
+    if dx_lowp is not None:
+        p.dx_lowp, p.lddx_lowp, p.lowp_dtype = dx_lowp.data_ptr(), _ld(dx_lowp), _dt(dx_lowp)
+    p.dgamma, p.dbeta, p.dbias = _ptr(dgamma), _ptr(dbeta), _ptr(dbias)
+    p.rows = int(x.shape[0] if rows is None else rows)
+    p.N = int(x.shape[1])
+    p.row_valid = _ptr(row_valid)
+    p.valid_pre, p.valid_post = int(valid_pre), int(valid_post)
+    p.dropout_out, p.dropout_in = dropout_out.c(), dropout_in.c()
+    L.check(L.load().clg_layernorm_bwd(C.byref(p), _stream()), "clg_layernorm_bwd")
+    _count()
+
+
+def attention_fwd(qkv, key_bias, ctx, lse, B, S, H, scale, dropout: DropSite = NO_DROP):
+    _need_cuda(qkv, key_bias, ctx)
+    p = L.AttentionFwdParams()
+    p.qkv, p.ld_qkv = qkv.data_ptr(), _ld(qkv)
+    p.key_bias = key_bias.data_ptr()
+    p.ctx, p.ld_ctx = ctx.data_ptr(), _ld(ctx)
+    p.lse = _ptr(lse)
+    p.dtype = _dt(qkv)
+    p.B, p.S, p.H = int(B), int(S), int(H)
+    p.scale = float(scale)
+    p.dropout = dropout.c()
+    L.check(L.load().clg_attention_fwd(C.byref(p), _stream()), "clg_attention_fwd")
+    _count()
+
+
+def attention_bwd(qkv, key_bias, ctx, dctx, lse, dqkv, B, S, H, scale, dropout: DropSite = NO_DROP):
+    _need_cuda(qkv, key_bias, ctx, dctx, lse, dqkv)
+    p = L.AttentionBwdParams()
+    p.qkv, p.ld_qkv = qkv.data_ptr(), _ld(qkv)
+    p.key_bias = key_bias.data_ptr()
+    p.ctx, p.ld_ctx = ctx.data_ptr(), _ld(ctx)
+    p.dctx, p.ld_dctx = dctx.data_ptr(), _ld(dctx)
+    p.lse = lse.data_ptr()
+    p.dqkv, p.ld_dqkv = dqkv.data_ptr(), _ld(dqkv)
+    p.dtype = _dt(qkv)
+    p.B, p.S, p.H = int(B), int(S), int(H)
+    p.scale = float(scale)
+    p.dropout = dropout.c()
+    L.check(L.load().clg_attention_bwd(C.byref(p), _stream()), "clg_attention_bwd")
+    _count()
+
+
+def embed_text_fwd(ids, seg, word, pos, type_tab, out, *, pad_id, out_map=None, pos_mode=0, pos_base=0):
+    _need_cuda(ids, word, out)
+    p = L.EmbedTextParams()
+    p.ids, p.seg = ids.data_ptr(), _ptr(seg)
+    p.word, p.pos, p.type = word.data_ptr(), _ptr(pos), _ptr(type_tab)
+    p.out, p.ld_out = out.data_ptr(), _ld(out)
+    if out_map is not None:
+        p.out_map = out_map
+    p.B, p.T, p.N, p.pad_id = int(ids.shape[0]), int(ids.shape[1]), int(word.shape[1]), int(pad_id)
+    p.pos_mode, p.pos_base, p.vocab = int(pos_mode), int(pos_base), int(word.shape[0])
+    L.check(L.load().clg_embed_text_fwd(C.byref(p), _stream()), "clg_embed_text_fwd")
+    _count()
+
+
+def embed_text_bwd(ids, seg, dout, dword, dpos, dtype_tab, *, pad_id, dout_map=None, pos_mode=0, pos_base=0, N=None):
+    _need_cuda(ids, dout)
+    p = L.EmbedTextBwdParams()
+    p.ids, p.seg = ids.data_ptr(), _ptr(seg)
+    p.dout, p.ld_dout = dout.data_ptr(), _ld(dout)
+    if dout_map is not None:
+        p.dout_map = dout_map
+    p.dword, p.dpos, p.dtype_tab = _ptr(dword), _ptr(dpos), _ptr(dtype_tab)
+    p.B, p.T, p.pad_id = int(ids.shape[0]), int(ids.shape[1]), int(pad_id)
+    p.N = int(dout.shape[1] if N is None else N)
+    p.pos_mode, p.pos_base = int(pos_mode), int(pos_base)
+    p.vocab = int(dword.shape[0]) if dword is not None else 0
+    L.check(L.load().clg_embed_text_bwd(C.byref(p), _stream()), "clg_embed_text_bwd")
+    _count()
+
+
+def gqa_prior_loss(logits, target, dist, *, dlogits=None, row_buf, out, pred=None, topk=10, lam=10.0,
+                   gscale=1.0, score_mean=True):
+    _need_cuda(logits, target, row_buf, out)
+    p = L.GqaLossParams()
+    p.logits, p.ld_logits = logits.data_ptr(), _ld(logits)
+    p.target, p.ld_target = target.data_ptr(), _ld(target)
+    if dist is not None:
+        p.dist, p.ld_dist = dist.data_ptr(), _ld(dist)
+    if dlogits is not None:
+        p.dlogits, p.ld_dlogits = dlogits.data_ptr(), _ld(dlogits)
+    p.row_buf, p.out, p.pred = row_buf.data_ptr(), out.data_ptr(), _ptr(pred)
+    p.B, p.A, p.topk = int(logits.shape[0]), int(logits.shape[1]), int(topk)
+    p.lambda_, p.gscale, p.score_mean = float(lam), float(gscale), int(bool(score_mean))
+    L.check(L.load().clg_gqa_prior_loss(C.byref(p), _stream()), "clg_gqa_prior_loss")
+    _count(2)
+
+
+def sumsq(g_flat, partials, out):
+    _need_cuda(g_flat, partials, out)
+    L.check(L.load().clg_sumsq(g_flat.data_ptr(), g_flat.numel(), partials.data_ptr(), partials.numel(),
+                               out.data_ptr(), _stream()), "clg_sumsq")
+    _count(2)
+
+
+def adamw_step(p_flat, g_flat, m_flat, v_flat, chunk_tensor, tensors_dev, *, sumsq=None, max_norm=1.0, gscale=1.0,
+               beta1=0.9, beta2=0.999, eps=1e-6, bias_c1=1.0, bias_c2=1.0, shadow=None, mask_bits=None):
+    _need_cuda(p_flat, g_flat, m_flat, v_flat, chunk_tensor, tensors_dev)
+    p = L.AdamWParams()
+    p.p, p.g, p.m, p.v = p_flat.data_ptr(), g_flat.data_ptr(), m_flat.data_ptr(), v_flat.data_ptr()
+    p.n = p_flat.numel()
+    p.chunk_tensor, p.tensors = chunk_tensor.data_ptr(), tensors_dev.data_ptr()
+    p.sumsq = _ptr(sumsq)
+    p.max_norm, p.gscale = float(max_norm), float(gscale)
+    p.beta1, p.beta2, p.eps = float(beta1), float(beta2), float(eps)
+    p.bias_c1, p.bias_c2 = float(bias_c1), float(bias_c2)
+    p.shadow, p.mask_bits = _ptr(shadow), _ptr(mask_bits)
+    L.check(L.load().clg_adamw_step(C.byref(p), _stream()), "clg_adamw_step")
+    _count()
+
+
+def cast_shadow(p_flat, chunk_tensor, tensors_dev, shadow, mask_bits=None):
+    _need_cuda(p_flat, chunk_tensor, tensors_dev, shadow)
+    L.check(L.load().clg_cast_shadow(p_flat.data_ptr(), p_flat.numel(), chunk_tensor.data_ptr(), tensors_dev.data_ptr(),
+                                     shadow.data_ptr(), _ptr(mask_bits), _stream()), "clg_cast_shadow")
+    _count()
+
+
+def cast_f32_to_bf16(src, dst):
+    _need_cuda(src, dst)
+    L.check(L.load().clg_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "clg_cast_f32_to_bf16")
+    _count()
+
+
+def pack_mask(mask, bits, n=None):
+    _need_cuda(mask, bits)
+    L.check(L.load().clg_pack_mask(mask.data_ptr(), bits.data_ptr(), mask.numel() if n is None else n, _stream()), "clg_pack_mask")
+    _count()
+
+
+def apply_mask(w, bits, n=None):
+    _need_cuda(w, bits)
+    L.check(L.load().clg_apply_mask(w.data_ptr(), bits.data_ptr(), w.numel() if n is None else n, _stream()), "clg_apply_mask")
+    _count()
+
+
+def colsum(x, out, M=None, N=None):
+    _need_cuda(x, out)
+    L.check(L.load().clg_colsum(x.data_ptr(), _dt(x), _ld(x), int(x.shape[0] if M is None else M),
+                                int(x.shape[1] if N is None else N), out.data_ptr(), _stream()), "clg_colsum")
+    _count()
+
+
+def build_key_bias(txt_mask, img_mask, key_bias, row_valid=None, m3p_prefix=False):
+    _need_cuda(txt_mask, img_mask, key_bias)
+    B, T = txt_mask.shape
+    R = img_mask.shape[1]
+    L.check(L.load().clg_build_key_bias(txt_mask.data_ptr(), img_mask.data_ptr(), B, T, R, int(m3p_prefix),
+                                        key_bias.data_ptr(), _ptr(row_valid), _stream()), "clg_build_key_bias")
+    _count()
+
+
+def dropout_inplace(x, site: DropSite):
+    _need_cuda(x)
+    if site.p <= 0:
+        return
+    d = site.c()
+    L.check(L.load().clg_dropout_inplace(x.data_ptr(), x.numel(), C.byref(d), _stream()), "clg_dropout_inplace")
+    _count()
+
+
+def device_check(device: int = 0):
+    L.check(L.load().clg_device_check(device), "clg_device_check")
