@@ -171,6 +171,7 @@ SYMBOLS = {
     "clg_colsum": (C.c_int, [c_vp, c_i32, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "clg_build_key_bias": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "clg_dropout_inplace": (C.c_int, [c_vp, c_i64, C.POINTER(Dropout), c_vp]),
+    "clg_act_bwd": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
 }
 for _n in _SIZEOF_CHECKS:
     SYMBOLS[_n] = (C.c_size_t, [])

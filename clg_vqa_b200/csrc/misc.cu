@@ -93,6 +93,18 @@ __global__ void dropout_inplace_kernel(float* __restrict__ x, int64_t n, const D
     x[i] = drop_apply(d, (uint64_t)i, x[i]);
 }
 
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ aux, float* __restrict__ out,
+                               int64_t n, int act) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = aux[i];
+    float d = dy[i];
+    if (act == CLG_ACT_DGELU) d *= dgelu_erf(a);
+    else if (act == CLG_ACT_DRELU) d = a > 0.f ? d : 0.f;
+    else if (act == CLG_ACT_DTANH) d *= (1.f - a * a);
+    out[i] = d;
+  }
+}
+
 static int ew_grid(int64_t work_items, int threads) {
   int64_t g = (work_items + threads - 1) / threads;
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -168,4 +180,14 @@ extern "C" int clg_dropout_inplace(float* x, int64_t n, const clgDropout* d, clg
   if (n == 0 || d->p <= 0.f) return CLG_OK;
   dropout_inplace_kernel<<<ew_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, make_drop(*d));
   return check_launch("dropout_inplace_kernel");
+}
+
+extern "C" int clg_act_bwd(const float* dy, const float* aux, float* out, int64_t n, int32_t act, clgStream_t stream) {
+  using namespace clg;
+  if (!dy || !aux || !out || n < 0) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  if (n == 0) return CLG_OK;
+  act_bwd_kernel<<<ew_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, aux, out, n, act);
+  return check_launch("act_bwd_kernel");
 }

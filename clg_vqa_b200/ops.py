@@ -19,6 +19,14 @@ def launch_count() -> int:
     return _launches
 
 
+_gemm_timing = None   # when set to a list, tcgen05 GEMM launches append (start_event, end_event, flops)
+
+
+def set_gemm_timing(rec):
+    global _gemm_timing
+    _gemm_timing = rec
+
+
 def _count(n=1):
     global _launches
     _launches += n
@@ -101,6 +109,20 @@ def gemm(a, b, c, *, a_kmajor=True, b_kmajor=True, M=None, N=None, K=None, alpha
     p.drop_before_act = int(bool(drop_before_act))
     p.dropout = dropout.c()
     p.backend, p.split_k = int(backend), int(split_k)
+    rec = _gemm_timing
+    if rec is not None:
+        # same predicate as clg_gemm's auto dispatch: these launches run gemm_tc_kernel
+        is_tc = (backend != GEMM_SIMT and p.a_dtype == CLG_BF16 and p.b_dtype == CLG_BF16 and
+                 (backend == GEMM_TC or (M >= 128 and N >= 64 and K >= 64)) and p.lda % 8 == 0 and p.ldb % 8 == 0)
+        if is_tc:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.check(L.load().clg_gemm(C.byref(p), _stream()), "clg_gemm")
+            e1.record()
+            rec.append((e0, e1, 2.0 * M * N * K))
+            _count()
+            return c
     L.check(L.load().clg_gemm(C.byref(p), _stream()), "clg_gemm")
     _count()
     return c
@@ -308,6 +330,12 @@ def dropout_inplace(x, site: DropSite):
         return
     d = site.c()
     L.check(L.load().clg_dropout_inplace(x.data_ptr(), x.numel(), C.byref(d), _stream()), "clg_dropout_inplace")
+    _count()
+
+
+def act_bwd(dy, aux, out, act):
+    _need_cuda(dy, aux, out)
+    L.check(L.load().clg_act_bwd(dy.data_ptr(), aux.data_ptr(), out.data_ptr(), dy.numel(), int(act), _stream()), "clg_act_bwd")
     _count()
 
 

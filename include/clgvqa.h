@@ -327,6 +327,10 @@ int clg_build_key_bias(const int64_t* txt_mask, const int64_t* img_mask, int32_t
  * and its backward (same call on the gradient) */
 int clg_dropout_inplace(float* x, int64_t n, const clgDropout* d, clgStream_t stream);
 
+/* out[i] = dy[i] * act'(aux[i]) for the D* activations (classifier GeLU backward, encoders.py:L788-815);
+ * all fp32, out may alias dy */
+int clg_act_bwd(const float* dy, const float* aux, float* out, int64_t n, int32_t act, clgStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
