@@ -157,6 +157,7 @@ SYMBOLS = {
     "clg_gemm": (C.c_int, [C.POINTER(GemmParams), c_vp]),
     "clg_layernorm_fwd": (C.c_int, [C.POINTER(LayerNormFwdParams), c_vp]),
     "clg_layernorm_bwd": (C.c_int, [C.POINTER(LayerNormBwdParams), c_vp]),
+    "clg_set_attention_backend": (C.c_int, [C.c_int]),
     "clg_attention_fwd": (C.c_int, [C.POINTER(AttentionFwdParams), c_vp]),
     "clg_attention_bwd": (C.c_int, [C.POINTER(AttentionBwdParams), c_vp]),
     "clg_embed_text_fwd": (C.c_int, [C.POINTER(EmbedTextParams), c_vp]),

@@ -260,7 +260,13 @@ template <typename K> static int set_smem(K kernel, size_t bytes, const char* wh
   return CLG_OK;
 }
 
+int attention_tc_fwd(const clgAttentionFwdParams& p, cudaStream_t stream);
+int attention_tc_bwd(const clgAttentionBwdParams& p, cudaStream_t stream);
+static int g_attn_backend = 0;   // 0 auto (tcgen05 when bf16), 1 force FFMA
+
 }  // namespace clg
+
+extern "C" int clg_set_attention_backend(int backend) { clg::g_attn_backend = backend; return CLG_OK; }
 
 extern "C" int clg_attention_fwd(const clgAttentionFwdParams* p, clgStream_t stream) {
   using namespace clg;
@@ -268,6 +274,10 @@ extern "C" int clg_attention_fwd(const clgAttentionFwdParams* p, clgStream_t str
   int st = require_sm100();
   if (st != CLG_OK) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->dtype == CLG_BF16 && g_attn_backend == 0) {
+    st = attention_tc_fwd(*p, s);
+    if (st != CLG_ERR_UNSUPPORTED) return st;
+  }
   const size_t smem = fwd_smem(p->S);
   const Drop d = make_drop(p->dropout);
   dim3 grid(p->H, p->B);
@@ -291,6 +301,10 @@ extern "C" int clg_attention_bwd(const clgAttentionBwdParams* p, clgStream_t str
   int st = require_sm100();
   if (st != CLG_OK) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->dtype == CLG_BF16 && g_attn_backend == 0) {
+    st = attention_tc_bwd(*p, s);
+    if (st != CLG_ERR_UNSUPPORTED) return st;
+  }
   const size_t smem = bwd_smem(p->S);
   const Drop d = make_drop(p->dropout);
   dim3 grid(p->H, p->B);

@@ -9,9 +9,9 @@
 // (dgrad on W[N,K] as stored, wgrad on dY / X as stored) - selected by the UMMA descriptors, no
 // transposes in memory.  Optional split-K (atomic fp32 accumulate) for the wgrad shapes whose output
 // has too few tiles to fill 148 SMs.
-#include <cuda.h>
 #include <mutex>
 #include "gemm_epilogue.cuh"
+#include "tc_common.cuh"
 
 namespace clg {
 
@@ -29,82 +29,7 @@ template <int BN> struct TileCfg {
   static constexpr int SMEM_BYTES = KSTAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-// ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// UMMA shared-memory descriptor (sm_100): start address, leading / stride byte offsets (>>4),
-// version = 1 (bits 46-47), layout = SWIZZLE_128B (2) in bits 61-63.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-// instruction descriptor for kind::f16: D = F32 (bit 4), A = B = BF16 (bits 7, 10),
-// a_major (bit 15) / b_major (bit 16): 0 = K-major, 1 = MN-major; N>>3 at bits 17-22; M>>4 at 24-28.
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) { return make_idesc_mn(BM, n, a_mn, b_mn); }
 
 struct TcArgs {
   int M, N, K;
@@ -274,7 +199,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 tensor [outer, inner] with row pitch ld elements; box = 64 x box_outer, 128B swizzle.
-static int make_tmap(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+int make_tmap_bf16(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return CLG_ERR_CUDA;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return CLG_ERR_UNSUPPORTED;
@@ -302,11 +227,11 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
 
   CUtensorMap ta, tb;
   int st;
-  if (A_K) st = make_tmap(&ta, p.A, p.K, p.M, p.lda, BM);
-  else     st = make_tmap(&ta, p.A, p.M, p.K, p.lda, BK);
+  if (A_K) st = make_tmap_bf16(&ta, p.A, p.K, p.M, p.lda, BM);
+  else     st = make_tmap_bf16(&ta, p.A, p.M, p.K, p.lda, BK);
   if (st != CLG_OK) return st;
-  if (B_K) st = make_tmap(&tb, p.B, p.K, p.N, p.ldb, BN);
-  else     st = make_tmap(&tb, p.B, p.N, p.K, p.ldb, BK);
+  if (B_K) st = make_tmap_bf16(&tb, p.B, p.K, p.N, p.ldb, BN);
+  else     st = make_tmap_bf16(&tb, p.B, p.N, p.K, p.ldb, BK);
   if (st != CLG_OK) return st;
 
   TcArgs t;

@@ -181,6 +181,11 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx=None, dx_lowp=None, dgamma=Non
     _count()
 
 
+def set_attention_backend(backend: int):
+    """0 = auto (tcgen05 for bf16), 1 = force the FFMA kernel (debug / cross-check)"""
+    L.check(L.load().clg_set_attention_backend(int(backend)), "clg_set_attention_backend")
+
+
 def attention_fwd(qkv, key_bias, ctx, lse, B, S, H, scale, dropout: DropSite = NO_DROP):
     _need_cuda(qkv, key_bias, ctx)
     p = L.AttentionFwdParams()

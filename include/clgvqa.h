@@ -209,6 +209,8 @@ typedef struct {
   clgDropout dropout;
 } clgAttentionBwdParams;
 
+/* 0 = auto (tcgen05 kernels for bf16, FFMA kernel for fp32 / unsupported shapes), 1 = force the FFMA kernel */
+int clg_set_attention_backend(int backend);
 int clg_attention_fwd(const clgAttentionFwdParams* p, clgStream_t stream);
 int clg_attention_bwd(const clgAttentionBwdParams* p, clgStream_t stream);
 size_t clg_sizeof_attention_fwd_params(void);

@@ -458,3 +458,33 @@ def test_utilities():
     w2 = w.clone()
     ops.apply_mask(w2, bits)
     assert torch.equal(w2, w * mask)
+
+
+@pytest.mark.parametrize("S", [76, 140, 128, 33])
+def test_attention_tc_matches_ffma(S):
+    """tcgen05 attention (bf16) against the FFMA kernel on the same inputs, incl. identical dropout masks."""
+    B, H = 5, 12
+    D = H * 64
+    qkv = _rand(B * S, 3 * D, dtype=torch.bfloat16, seed=90)
+    nvalid = torch.tensor([S, S - 3, max(1, S // 2), S, 7][:B], device=DEV)
+    valid = torch.arange(S, device=DEV)[None, :] < nvalid[:, None]
+    kb = torch.where(valid, 0.0, -10000.0).float().contiguous()
+    dctx = _rand(B * S, D, dtype=torch.bfloat16, seed=91)
+    outs = {}
+    for backend in (0, 1):
+        ops.set_attention_backend(backend)
+        for site in (ops.NO_DROP, DropSite(0.1, 5, 1 << 41)):
+            ctx = torch.zeros(B * S, D, device=DEV, dtype=torch.bfloat16)
+            lse = torch.zeros(B, H, S, device=DEV)
+            dqkv = torch.zeros_like(qkv)
+            ops.attention_fwd(qkv, kb, ctx, lse, B, S, H, 0.125, site)
+            ops.attention_bwd(qkv, kb, ctx, dctx, lse, dqkv, B, S, H, 0.125, site)
+            outs[(backend, site.p)] = (ctx.float(), lse, dqkv.float())
+    ops.set_attention_backend(0)
+    for pdrop in (0.0, 0.1):
+        c0, l0, d0 = outs[(0, pdrop)]
+        c1, l1, d1 = outs[(1, pdrop)]
+        assert _rel(l0, l1) < 1e-5
+        assert _rel(c0, c1) < 1.5e-2
+        assert _rel(d0, d1) < 3e-2
+    assert torch.isfinite(outs[(0, 0.1)][2]).all()
