@@ -32,7 +32,10 @@ _BERT_DEFAULTS = dict(
 )
 
 _M3P_DEFAULTS = dict(_BERT_DEFAULTS)
-_M3P_DEFAULTS.update(n_heads=12, n_layers=12, image_embeddings="m3p", model="roberta")
+_M3P_DEFAULTS.update(n_heads=12, n_layers=12, image_embeddings="m3p", model="roberta", n_words=250002, emb_dim=768,
+                     n_langs=100, refine_layers=6, pad_index=1, dropout=0.1, attention_dropout=0.1, vocab_size=250002,
+                     pad_token_id=1, type_vocab_size=1, fusion_method="text", clf_hidden_size=1536, num_locs=5,
+                     norm_embeddings=True)
 
 
 class _Config:

@@ -28,36 +28,43 @@ int require_sm100();           // CLG_OK or CLG_ERR_ARCH for the current device 
 // ---------------------------------------------------------------------------------------------
 // dropout: counter-based hash, shared by all kernels (forward and backward regenerate the mask)
 // ---------------------------------------------------------------------------------------------
+// Element idx of a site draws 16 random bits: the low / high half of lowbias32((idx >> 1) ^ key),
+// key = 32-bit mix of (seed, site offset).  Kept iff bits >= p * 2^16 (p is quantised to 1/65536 and
+// the kept values are scaled by the exact 1/(1 - p_quantised)).  ~8 integer instructions per element.
 struct Drop {
-  uint32_t thresh;   // keep iff hash >= thresh
-  float scale;       // 1/(1-p)
-  uint64_t seed;
-  uint64_t offset;
+  uint32_t thresh;   // keep iff 16-bit draw >= thresh
+  float scale;       // 1/(1-p_q)
+  uint32_t key;
   bool on;
 };
+
+__host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU;
+  x ^= x >> 15; x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
+}
 
 __host__ __device__ inline Drop make_drop(const clgDropout& d) {
   Drop r;
   r.on = d.p > 0.f;
-  double t = (double)d.p * 4294967296.0;
-  r.thresh = r.on ? (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t) : 0u;
-  r.scale = r.on ? 1.0f / (1.0f - d.p) : 1.0f;
-  r.seed = d.seed;
-  r.offset = d.offset;
+  uint32_t t = r.on ? (uint32_t)(d.p * 65536.0f + 0.5f) : 0u;
+  if (t > 65535u) t = 65535u;
+  r.thresh = t;
+  r.scale = r.on ? 65536.0f / (float)(65536u - t) : 1.0f;
+  uint64_t z = (d.seed + 0x9E3779B97F4A7C15ULL) * 0xBF58476D1CE4E5B9ULL;
+  z ^= (d.offset + 0x94D049BB133111EBULL) * 0xD6E8FEB86659FD93ULL;
+  z ^= z >> 32;
+  r.key = lowbias32((uint32_t)z);
   return r;
 }
 
-__host__ __device__ __forceinline__ uint32_t mix64to32(uint64_t z) {
-  z ^= z >> 33; z *= 0xff51afd7ed558ccdULL;
-  z ^= z >> 33; z *= 0xc4ceb9fe1a85ec53ULL;
-  z ^= z >> 33;
-  return (uint32_t)z;
-}
-
-// keep-mask for element idx of a site
+// keep-mask for element idx of a site (idx < 2^32 for every site of this model)
 __host__ __device__ __forceinline__ bool drop_keep(const Drop& d, uint64_t idx) {
-  uint64_t z = (d.offset + idx) * 0x9E3779B97F4A7C15ULL + d.seed;
-  return mix64to32(z) >= d.thresh;
+  const uint32_t i = (uint32_t)idx;
+  const uint32_t h = lowbias32((i >> 1) ^ d.key);
+  const uint32_t r = (i & 1u) ? (h >> 16) : (h & 0xffffu);
+  return r >= d.thresh;
 }
 
 __host__ __device__ __forceinline__ float drop_apply(const Drop& d, uint64_t idx, float v) {

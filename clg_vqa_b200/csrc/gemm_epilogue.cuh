@@ -74,7 +74,7 @@ __device__ __forceinline__ void epi_row_chunk(const EpiArgs& e, int row, int col
   if (ncols <= 0) return;
   float v[W];
   const bool full = (ncols == W);
-  const bool simple = full && !e.drop.on && !e.mask_bits &&
+  const bool simple = full &&
                       (e.act == CLG_ACT_NONE || e.act == CLG_ACT_GELU || e.act == CLG_ACT_DGELU) &&
                       ((col0 & 7) == 0) && ((e.ldc & 7) == 0);
   if (simple) {
@@ -87,6 +87,11 @@ __device__ __forceinline__ void epi_row_chunk(const EpiArgs& e, int row, int col
         const float4 b = __ldg(b4 + j);
         v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
       }
+    }
+    const uint64_t eidx = (uint64_t)row * (uint64_t)e.N + (uint64_t)col0;
+    if (e.drop.on && e.drop_before_act) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) v[j] = drop_keep(e.drop, eidx + j) ? v[j] * e.drop.scale : 0.f;
     }
     if (e.act == CLG_ACT_GELU) {
       if (e.aux_out) {
@@ -131,6 +136,10 @@ __device__ __forceinline__ void epi_row_chunk(const EpiArgs& e, int row, int col
           v[j] *= dgelu_erf(load_as_f32(e.aux_in, e.aux_in_dtype, (int64_t)row * e.ld_aux_in + col0 + j));
       }
     }
+    if (e.drop.on && !e.drop_before_act) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) v[j] = drop_keep(e.drop, eidx + j) ? v[j] * e.drop.scale : 0.f;
+    }
     if (e.residual) {
       if ((e.ld_res & 3) == 0) {
         const float4* r4 = reinterpret_cast<const float4*>(e.residual + (int64_t)row * e.ld_res + col0);
@@ -142,6 +151,19 @@ __device__ __forceinline__ void epi_row_chunk(const EpiArgs& e, int row, int col
       } else {
 #pragma unroll
         for (int j = 0; j < W; ++j) v[j] += __ldg(e.residual + (int64_t)row * e.ld_res + col0 + j);
+      }
+    }
+    if (e.mask_bits) {
+      if ((eidx & 31) == 0 && (W % 32) == 0) {
+#pragma unroll
+        for (int w = 0; w < W / 32; ++w) {
+          const uint32_t word = __ldg(e.mask_bits + (eidx >> 5) + w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[32 * w + j] *= ((word >> j) & 1u) ? 1.f : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) v[j] *= mask_bit(e.mask_bits, (int64_t)(eidx + j)) ? 1.f : 0.f;
       }
     }
     if (e.c_dtype == CLG_BF16) {

@@ -10,7 +10,7 @@ static constexpr int SBM = 64, SBN = 128, SBK = 16;
 template <typename TA, typename TB>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const TA* __restrict__ A, const TB* __restrict__ B, int M, int N, int K, int64_t lda, int64_t ldb,
-                 int a_k, int b_k, const EpiArgs e) {
+                 int a_k, int b_k, int k_per_split, const EpiArgs e) {
   __shared__ float As[SBK][SBM + 4];
   __shared__ float Bs[SBK][SBN + 4];
   const int tid = threadIdx.x;
@@ -22,7 +22,10 @@ gemm_simt_kernel(const TA* __restrict__ A, const TB* __restrict__ B, int M, int 
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += SBK) {
+  const int k_lo = blockIdx.z * k_per_split;
+  const int k_hi = min(K, k_lo + k_per_split);
+  K = k_hi;
+  for (int k0 = k_lo; k0 < k_hi; k0 += SBK) {
     // A tile: 64 x 16
 #pragma unroll
     for (int it = 0; it < (SBM * SBK) / 256; ++it) {
@@ -65,10 +68,29 @@ gemm_simt_kernel(const TA* __restrict__ A, const TB* __restrict__ B, int M, int 
 
 template <typename TA, typename TB>
 static int launch_simt(const clgGemmParams& p, cudaStream_t s) {
-  const EpiArgs e = make_epi(p);
+  EpiArgs e = make_epi(p);
   dim3 grid((p.N + SBN - 1) / SBN, (p.M + SBM - 1) / SBM);
+  // split-K (atomic fp32 accumulate) for long reductions with too few output tiles (e.g. dW_loc [768 x 7])
+  int splits = 1;
+  const int tiles = grid.x * grid.y;
+  const bool can_split = p.act == CLG_ACT_NONE && !p.bias && !p.residual && p.c_dtype == CLG_F32 && p.dropout.p <= 0.f;
+  if (can_split && tiles * 2 <= num_sms() && p.K >= 1024) {
+    splits = (2 * num_sms()) / tiles;
+    const int max_s = p.K / 256;
+    if (splits > max_s) splits = max_s;
+    if (splits < 1) splits = 1;
+  }
+  int kper = (p.K + splits - 1) / splits;
+  kper = (kper + SBK - 1) / SBK * SBK;
+  splits = (p.K + kper - 1) / kper;
+  if (splits > 1) {
+    if (!p.accumulate)
+      CLG_CUDA_OK(cudaMemset2DAsync(p.C, p.ldc * sizeof(float), 0, (size_t)p.N * sizeof(float), p.M, s), "memset(simt split-K)");
+    e.accumulate = 2;
+  }
+  grid.z = splits;
   gemm_simt_kernel<TA, TB><<<grid, 256, 0, s>>>((const TA*)p.A, (const TB*)p.B, p.M, p.N, p.K, p.lda, p.ldb,
-                                                p.a_kmajor, p.b_kmajor, e);
+                                                p.a_kmajor, p.b_kmajor, kper, e);
   return check_launch("gemm_simt_kernel");
 }
 

@@ -39,7 +39,52 @@ __global__ void apply_mask_kernel(float* __restrict__ w, const uint32_t* __restr
     w[i] *= mask_bit(bits, i) ? 1.f : 0.f;
 }
 
-// out[n] += sum_m X[m, n]; block = 32 x 8 threads, each block owns 32 columns and a slab of rows
+// out[n] += sum_m X[m, n]: block = 32 x 8 threads; a thread owns 8 consecutive columns (one 16 B /
+// two 16 B loads per row), the 8 y-slices stride over the rows of the block's slab.
+template <typename T> struct Vec8 { };
+template <> struct Vec8<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float* v) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { const float2 f = __bfloat1622float2(h[t]); v[2 * t] = f.x; v[2 * t + 1] = f.y; }
+  }
+};
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
+template <typename T>
+__global__ void colsum_vec_kernel(const T* __restrict__ x, int64_t ld, int M, int N, float* __restrict__ out, int rows_per_block) {
+  __shared__ float red[8][256 + 8];
+  const int col = blockIdx.x * 256 + threadIdx.x * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < N) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      float v[8];
+      Vec8<T>::load(x + (int64_t)r * ld + col, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;      // 256 threads -> 256 columns
+  const int c = blockIdx.x * 256 + t;
+  if (c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += red[j][t];
+    atomicAdd(out + c, s);
+  }
+}
+
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, int M, int N, float* __restrict__ out, int rows_per_block) {
   __shared__ float red[8][33];
@@ -150,15 +195,23 @@ extern "C" int clg_colsum(const void* x, int32_t dtype, int64_t ld, int32_t M, i
   if (!x || !out || M <= 0 || N <= 0) return CLG_ERR_ARG;
   int st = require_sm100();
   if (st != CLG_OK) return st;
-  const int col_blocks = (N + 31) / 32;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int esz = dtype == CLG_BF16 ? 2 : 4;
+  const bool vec = (N % 8 == 0) && ((ld * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const int cw = vec ? 256 : 32;
+  const int col_blocks = (N + cw - 1) / cw;
   int row_blocks = (num_sms() * 4 + col_blocks - 1) / col_blocks;
   if (row_blocks > (M + 63) / 64) row_blocks = (M + 63) / 64;
   if (row_blocks < 1) row_blocks = 1;
   const int rows_per_block = (M + row_blocks - 1) / row_blocks;
   dim3 grid(col_blocks, row_blocks), block(32, 8);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (dtype == CLG_BF16) colsum_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, ld, M, N, out, rows_per_block);
-  else colsum_kernel<float><<<grid, block, 0, s>>>((const float*)x, ld, M, N, out, rows_per_block);
+  if (vec) {
+    if (dtype == CLG_BF16) colsum_vec_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, ld, M, N, out, rows_per_block);
+    else colsum_vec_kernel<float><<<grid, block, 0, s>>>((const float*)x, ld, M, N, out, rows_per_block);
+  } else {
+    if (dtype == CLG_BF16) colsum_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, ld, M, N, out, rows_per_block);
+    else colsum_kernel<float><<<grid, block, 0, s>>>((const float*)x, ld, M, N, out, rows_per_block);
+  }
   return check_launch("colsum_kernel");
 }
 

@@ -330,3 +330,50 @@ class BertForVLTasks(_VLTasksBase):
         logits = self._get_engine().run(input_txt, input_imgs, image_loc, task_id, token_type_ids, attention_mask,
                                         image_attention_mask)
         return logits, None, None, ([None], [None])
+
+
+# ------------------------------------------------------------------------------------------------
+# M3P
+# ------------------------------------------------------------------------------------------------
+class M3PModel(nn.Module):
+    """encoders.py:L1024-1042: `encoder` = M3PTransformerModel (only jointfwd is used), `pooler` is the
+    SAME module object as encoder.pooled_layer (state_dict alias bert.pooler.* == bert.encoder.pooled_layer.*)."""
+
+    def __init__(self, config):
+        super().__init__()
+        from . import m3p_layout
+        self.encoder = m3p_layout.build_encoder(config)
+        self.pooler = self.encoder.pooled_layer
+
+
+class M3PForVLTasks(_VLTasksBase):
+    """encoders.py:L1262-1353"""
+    _family = "m3p"
+
+    def __init__(self, config, task_cfg, task_ids, dropout_prob=0.1):
+        super().__init__()
+        self.config = config
+        if int(getattr(config, "emb_dim", 768)) != 64 * int(getattr(config, "n_heads", 12)):
+            raise ValueError("clg_vqa_b200 implements 64-d attention heads (m3p_base.json: 768 / 12)")
+        self.bert = M3PModel(config)
+        self.dropout = nn.Dropout(dropout_prob)
+        self.task_cfg = task_cfg
+        self.clfs_dict = self._make_classifiers(config, task_cfg, task_ids)
+        self.fusion_method = getattr(config, "fusion_method", "text")
+        self.apply(self.init_weights)
+
+    def forward(self, input_txt, input_imgs, image_loc, task_id, token_type_ids=None, attention_mask=None,
+                image_attention_mask=None, output_all_encoded_layers=False, output_all_attention_masks=False):
+        if output_all_encoded_layers:
+            raise NotImplementedError("output_all_encoded_layers for M3P")      # encoders.py:L1351
+        if task_id not in self.clfs_dict:
+            raise KeyError(task_id)
+        if attention_mask is None:
+            attention_mask = torch.ones_like(input_txt)
+        if image_attention_mask is None:
+            image_attention_mask = torch.ones(input_imgs.size(0), input_imgs.size(1)).type_as(input_txt)
+        if token_type_ids is None:
+            token_type_ids = torch.zeros_like(input_txt)      # ignored by M3P (m3p_transformer.py:L877-964)
+        logits = self._get_engine().run(input_txt, input_imgs, image_loc, task_id, token_type_ids, attention_mask,
+                                        image_attention_mask)
+        return logits, None, None, None

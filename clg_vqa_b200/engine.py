@@ -212,6 +212,9 @@ class Engine:
                 shadow_off += _pad(s.numel)
                 mask_off += _pad(s.numel)
         self.slots = slots
+        if self.family == "m3p":
+            from . import engine_m3p
+            engine_m3p.mark_dead_slots(self)
         self.p_flat, self.g_flat = p_flat, g_flat
         self.total = total
         self.shadow = torch.zeros(max(shadow_off, CHUNK), dtype=torch.bfloat16, device=device)
@@ -578,7 +581,7 @@ class Engine:
                 o = s.start
                 for p in s.params:
                     n = p.numel()
-                    if p.requires_grad:
+                    if p.requires_grad and s.has_grad:
                         p.grad = self.g_flat[o:o + n].view(p.shape)
                     o += n
             self.grads_consumed = False
@@ -680,6 +683,8 @@ class Engine:
             self._layer_bwd(ws, lw, x_in, x_in_lp, ws["kb"], B, S, sa.query, so.dense, so.LayerNorm, fi.dense, fo.dense,
                             fo.LayerNorm, 0.125, self._site(2 + 4 * l, p_a, training), self._site(3 + 4 * l, p_h, training),
                             self._site(4 + 4 * l, p_h, training))
+            if self.dp is not None:
+                self.dp.layer_done(self, l)
         dx = ws["dx"]
         # ---- text embeddings
         ops.layernorm_bwd(dx, ws["e_txt"], E.LayerNorm.weight.data, ws["m_txt"], ws["r_txt"], dx=ws["de_txt"],
@@ -701,6 +706,34 @@ class Engine:
                           dbeta=self.grad_view(E.image_location_layer_norm.bias),
                           dbias=self._gvec(self.b_slot[id(E.image_location_embeddings)], d))
         self._wgrad(ws["dl"], sv["la"], E.image_location_embeddings, d, sv["la"].shape[1])
+
+    # ------------------------------------------------------------------------------------------
+    # hooks for the data-parallel exchange (parallel.GradExchange)
+    # ------------------------------------------------------------------------------------------
+    def word_table_param(self):
+        if self.family == "uc2":
+            return self.model.bert.embeddings.word_embeddings.weight
+        return self.model.bert.encoder.embeddings.weight
+
+    def word_grad_rows(self):
+        """(token ids [B*T], d(loss)/d(word rows) [B*T, d], replay(ids_r, rows_r)) of the last backward:
+        another rank's contribution to the word-embedding gradient is replayed with the same
+        scatter-add kernel instead of all-reducing the dense 250002 x 768 table."""
+        sv = self._saved
+        ws = sv["ws"]
+        B, T, R = sv["B"], sv["T"], sv["R"]
+        gword = self.grad_view(self.word_table_param())
+        if self.family == "uc2":
+            rows = ws["de_txt"]
+            pad = int(self.cfg.pad_token_id)
+        else:
+            rows = ws["de_joint"].view(B, T + R, self.d)[:, R:, :].reshape(B * T, self.d)
+            pad = int(getattr(self.cfg, "pad_index", 1))
+
+        def replay(ids_r, rows_r):
+            ops.embed_text_bwd(ids_r.view(B, T), None, rows_r, gword, None, None, pad_id=pad)
+
+        return sv["ids"].reshape(-1), rows, replay
 
     # ------------------------------------------------------------------------------------------
     # M3P (filled in by engine_m3p.py)

@@ -13,6 +13,8 @@ from clg_vqa_b200 import ops  # noqa: E402
 from clg_vqa_b200.ops import DropSite  # noqa: E402
 
 DEV = "cuda"
+PQ = round(0.1 * 65536) / 65536.0      # dropout probability as quantised by the kernels
+KEEP = 1.0 - PQ
 
 
 def _rand(*shape, dtype=torch.float32, scale=1.0, seed=0):
@@ -143,7 +145,7 @@ def test_gemm_dropout_consistency():
     kept = y1 != 0
     frac = float(kept.float().mean())
     assert abs(frac - 0.9) < 0.01
-    assert _rel(y1[kept], y0[kept] / 0.9) < 1e-5
+    assert _rel(y1[kept], y0[kept] / KEEP) < 1e-5
     y2 = torch.empty(M, N, device=DEV)
     ops.gemm(a, w, y2, dropout=site, backend=ops.GEMM_SIMT)       # same mask from both backends
     assert torch.equal(y2 != 0, kept)
@@ -230,16 +232,16 @@ def test_layernorm_dropout_sites():
     ops.layernorm_fwd(x, g, b, 1e-5, y=y1, dropout=out_site)
     keep = (y1 != 0) | (y0 == 0)
     assert abs(float(keep.float().mean()) - 0.9) < 0.01
-    assert _rel(y1[keep], y0[keep] / 0.9) < 1e-6
+    assert _rel(y1[keep], y0[keep] / KEEP) < 1e-6
     dy = _rand(rows, N, seed=43)
     dx_ref = torch.empty_like(x)
-    ops.layernorm_bwd(dy * keep / 0.9, x, g, mean, rstd, dx=dx_ref)
+    ops.layernorm_bwd((dy * keep / KEEP).contiguous(), x, g, mean, rstd, dx=dx_ref)
     dx = torch.empty_like(x); dxl = torch.empty_like(x)
     ops.layernorm_bwd(dy, x, g, mean, rstd, dx=dx, dx_lowp=dxl, dropout_out=out_site, dropout_in=in_site)
     assert _rel(dx, dx_ref) < 1e-6
     kin = dxl != 0
     assert abs(float(kin.float().mean()) - 0.9) < 0.01
-    assert _rel(dxl[kin], dx[kin] / 0.9) < 1e-6
+    assert _rel(dxl[kin], dx[kin] / KEEP) < 1e-6
 
 
 # ------------------------------------------------------------------------------------------------

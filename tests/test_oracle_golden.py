@@ -1,0 +1,130 @@
+"""CPU: pin the oracle against the golden fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py; /root/reference is not needed to run these).  Covers UC2 and M3P forward
+(fp32 / fp64 / bf16-operand shim), the GQA prior loss, per-parameter gradient norms and kept gradients.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from clg_vqa_b200 import config as C
+from clg_vqa_b200 import synthetic as S
+from oracle import loss_oracle, m3p_oracle, uc2_oracle
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    return g, json.loads(str(g["meta"]))
+
+
+def _rel(a, b):
+    a = torch.as_tensor(a).double()
+    b = torch.as_tensor(b).double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _setup(meta):
+    fam = meta["family"]
+    if fam == "uc2":
+        from clg_vqa_b200.encoders import BertForVLTasks
+        cfg = C.uc2_base(meta["layers"], vocab_size=meta["vocab"])
+        shapes = {k: tuple(v.shape) for k, v in BertForVLTasks(cfg, C.gqa_task_cfg(meta["R"]), ["TASK15"]).state_dict().items()}
+        fwd = uc2_oracle.uc2_forward
+    else:
+        from clg_vqa_b200 import m3p_layout
+        cfg = C.m3p_base(meta["layers"], n_words=meta.get("n_words", 250002))
+        shapes = m3p_layout.state_shapes(cfg, num_labels=1842)
+        fwd = m3p_oracle.m3p_forward
+    sd = S.synth_state_dict(shapes, seed=meta["weight_seed"])
+    b = S.synth_batch(meta["B"], num_regions=meta["R"], num_locs=7 if fam == "uc2" else 5, seed=meta["batch_seed"],
+                      ragged_regions=meta["ragged"], vocab_size=meta["vocab"], normalize=(fam == "m3p"))
+    chk = float(b["features"].double().sum() + b["spatials"].double().sum() + b["question"].double().sum())
+    assert abs(chk - meta["input_checksum"]) <= 1e-6 * abs(meta["input_checksum"])
+    return cfg, sd, b, fwd
+
+
+def _args(b, dtype=None):
+    f, s = b["features"], b["spatials"]
+    if dtype is not None:
+        f, s = f.to(dtype), s.to(dtype)
+    return (b["question"], f, s, b["segment_ids"], b["input_mask"], b["image_mask"])
+
+
+@pytest.mark.parametrize("case", ["uc2_L2_B4", "m3p_L2_B4"])
+def test_oracle_matches_reference_fp32_fp64_bf16shim(case):
+    g, meta = _load(case)
+    cfg, sd, b, fwd = _setup(meta)
+    with torch.no_grad():
+        lg = fwd(sd, cfg, *_args(b))
+        assert _rel(lg, g["logits_fp32"]) <= 5e-6
+        sd64 = {k: v.double() for k, v in sd.items()}
+        lg64 = fwd(sd64, cfg, *_args(b, torch.float64))
+        assert _rel(lg64, g["logits_fp64"]) <= 1e-10
+        lgb = fwd(sd, cfg, *_args(b), mm_dtype=torch.bfloat16)
+        assert _rel(lgb, g["logits_bf16shim"]) <= 5e-6
+        loss, score = loss_oracle.gqa_prior_loss(lg, b["target"], b["distances"], 10.0)
+    assert abs(float(loss) - float(g["loss_fp32"])) / float(g["loss_fp32"]) <= 1e-5
+    assert abs(float(score) - float(g["score_fp32"])) <= 1e-6
+
+
+def test_oracle_gradients_match_reference_uc2():
+    g, meta = _load("uc2_L2_B4")
+    cfg, sd, b, fwd = _setup(meta)
+    leaves = {}
+    for k in list(sd):
+        ck = S.canonical_key(k)
+        if ck not in leaves:
+            leaves[ck] = sd[ck].clone().requires_grad_(True)
+        sd[k] = leaves[ck]
+    lg = fwd(sd, cfg, *_args(b))
+    loss, _ = loss_oracle.gqa_prior_loss(lg, b["target"], b["distances"], 10.0)
+    loss.backward()
+    floor = 1e-3 * float(np.median(g["grad_norms"]))
+    for n, ref in zip([str(x) for x in g["grad_names"]], g["grad_norms"]):
+        mine = float(leaves[S.canonical_key(n)].grad.double().norm())
+        assert abs(mine - ref) / max(ref, floor) <= 1e-4, n
+    gscale = max(float(np.abs(g[k]).max()) for k in g.files if k.startswith("grad::"))
+    for key in g.files:
+        if key.startswith("grad::"):
+            a = leaves[S.canonical_key(key[6:])].grad.double()
+            r = torch.from_numpy(g[key]).double()
+            assert float((a - r).abs().max()) / max(float(r.abs().max()), 1e-3 * gscale) <= 1e-4, key
+    # closed-form d loss / d logits against autograd
+    z = lg.detach().double().requires_grad_(True)
+    l2, _ = loss_oracle.gqa_prior_loss(z, b["target"].double(), b["distances"].double(), 10.0)
+    l2.backward()
+    cf = loss_oracle.gqa_prior_loss_grad(z.detach(), b["target"].double(), b["distances"].double(), 10.0)
+    assert _rel(cf, z.grad) <= 1e-10
+
+
+def test_bf16_oracle_is_chaotic_at_1e3():
+    """Evidence for the bf16 tolerance (DESIGN.md 'bf16 parity'): the bf16-operand oracle with the SAME
+    rounding points but exact (fp64) accumulation already differs from the fp32-accumulate oracle by more
+    than the 1e-3 the north star asks for - the bound is not reachable by any pipeline whose accumulation
+    order differs from torch-CPU's."""
+    g, meta = _load("uc2_L2_B4")
+    cfg, sd, b, fwd = _setup(meta)
+    with torch.no_grad():
+        sd64 = {k: v.double() for k, v in sd.items()}
+        exact_acc = fwd(sd64, cfg, *_args(b, torch.float64), mm_dtype=torch.bfloat16)
+    err = _rel(exact_acc, g["logits_bf16shim"])
+    assert 1e-3 < err < 2e-2, err
+    assert _rel(g["logits_bf16shim"], g["logits_fp32"]) > 1e-3
+
+
+def test_loss_edge_cases():
+    A = 1842
+    torch.manual_seed(1)
+    z = torch.randn(3, A)
+    target = torch.zeros(3, A)
+    target[0, 7] = 1.0
+    target[1, 9] = 0.9          # truncates to 0 -> argmax over all-zero row = class 0
+    dist = torch.rand(3, A)
+    loss, score = loss_oracle.gqa_prior_loss(z, target, dist, 10.0)
+    y = torch.argmax(target.long(), 1)
+    assert y.tolist() == [7, 0, 0]
+    assert torch.isfinite(loss)

@@ -1,0 +1,70 @@
+"""CPU, world_size = 2, gloo: the data-parallel gradient exchange (clg_vqa_b200.parallel.GradExchange).
+N-rank result must equal the single-process result on the concatenated batch: dense ranges are
+sum-all-reduced in place, the word-embedding gradient is exchanged as (token ids, rows) and replayed,
+no_sync() suppresses communication during gradient accumulation."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from clg_vqa_b200.parallel import GradExchange
+        torch.manual_seed(100 + rank)
+        V, D, NTOK = 50, 8, 12
+        dense = torch.randn(4096)                       # stand-in for the dense part of the gradient arena
+        ids = torch.randint(0, V, (NTOK,))
+        rows = torch.randn(NTOK, D)
+        table = torch.zeros(V, D).index_add_(0, ids, rows)      # this rank's own word-table gradient
+        ex = GradExchange(world)
+        mine_dense = dense.clone()
+        # per-"layer" buckets launched early, remainder at the end
+        ex.reduce_range(mine_dense, 1024, 2048)
+        ex.reduce_range(mine_dense, 2048, 3072)
+        ex.reduce_range(mine_dense, 0, 1024)
+        ex.reduce_range(mine_dense, 3072, 4096)
+        ex.exchange_rows(ids, rows, lambda i, r: table.index_add_(0, i, r))
+        ex.finish()
+        # reference: gather everything and sum
+        all_dense = [torch.zeros_like(dense) for _ in range(world)]
+        dist.all_gather(all_dense, dense)
+        all_ids = [torch.zeros_like(ids) for _ in range(world)]
+        all_rows = [torch.zeros_like(rows) for _ in range(world)]
+        dist.all_gather(all_ids, ids)
+        dist.all_gather(all_rows, rows)
+        ref_table = torch.zeros(V, D)
+        for i, r in zip(all_ids, all_rows):
+            ref_table.index_add_(0, i, r)
+        ok = torch.allclose(mine_dense, sum(all_dense), atol=1e-6) and torch.allclose(table, ref_table, atol=1e-6)
+        # gradient accumulation: no communication inside no_sync()
+        with ex.no_sync():
+            keep = dense.clone()
+            ex.reduce_range(keep, 0, 4096)
+            ex.finish()
+        ok = ok and torch.equal(keep, dense)
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_exchange_world2_gloo():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
