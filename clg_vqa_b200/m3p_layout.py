@@ -81,7 +81,14 @@ def live_prefixes(cfg):
 
 
 class Holder(nn.Module):
-    """anonymous container; children are attached with add_module under the reference's names"""
+    """anonymous container; children are attached with add_module under the reference's names
+    (numeric names index like an nn.ModuleList)"""
+
+    def __getitem__(self, i):
+        return self._modules[str(i)]
+
+    def __len__(self):
+        return len(self._modules)
 
 
 def build_encoder(cfg) -> nn.Module:
