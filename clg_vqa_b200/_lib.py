@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libclgvqa.so")
 
 CLG_F32, CLG_BF16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH, ACT_DGELU, ACT_DRELU, ACT_DTANH = range(7)
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH, ACT_DGELU, ACT_DRELU, ACT_DTANH, ACT_GELU_GRAD, ACT_MUL_AUX = range(9)
 GEMM_AUTO, GEMM_TC, GEMM_SIMT = 0, 1, 2
 CHUNK = 2048
 

@@ -190,22 +190,25 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
 // ------------------------------------------------------------------------------------------------
 // backward (single query tile: S <= 128; S > 128 uses the FFMA kernel)
+// Shared memory holds only NP = ceil16(S) rows per operand tile and TMEM only 256 columns (the dV / dK /
+// dQ accumulators reuse the S / dP columns once those have been read), so two CTAs fit per SM.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(A_THREADS)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do, const AttnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const int NP = a.NP;                               // <= 128
-  const uint32_t T16 = QT * 128;                     // 16 KiB tile
-  const uint32_t sQ = base, sK = sQ + T16, sV = sK + T16, sdO = sV + T16;
-  const uint32_t sP = sdO + T16;                     // 2 x [128][64]: P_drop  (rows i, cols j)
-  const uint32_t sdS = sP + 2 * T16;                 // 2 x [128][64]: dS
-  const uint32_t sBar = sdS + 2 * T16;
+  const int NP = a.NP;                               // <= 128, multiple of 16
+  const uint32_t TN = (uint32_t)NP * 128u;           // bytes of one [NP][64] bf16 tile (multiple of 2 KiB)
+  const uint32_t sBar = base;                        // barriers, tmem slot, key bias (first KiB)
+  const uint32_t sQ = base + 1024, sK = sQ + TN, sV = sK + TN, sdO = sV + TN;
+  const uint32_t sP = sdO + TN;                      // 2 x [NP][64]: P_drop  (rows i, cols j)
+  const uint32_t sdS = sP + 2 * TN;                  // 2 x [NP][64]: dS      (+ 16 KiB slack behind it: the M = 128
+                                                     //  K-major reads of dS touch rows NP..127 of a block)
   uint8_t* gP = gen + (sP - base);
   uint8_t* gdS = gen + (sdS - base);
-  float* kb = reinterpret_cast<float*>(gen + (sBar - base) + 64);
-  volatile uint32_t* tslot = reinterpret_cast<volatile uint32_t*>(gen + (sBar - base) + 32);
+  float* kb = reinterpret_cast<float*>(gen + 64);
+  volatile uint32_t* tslot = reinterpret_cast<volatile uint32_t*>(gen + 32);
   const uint32_t bar_tma = sBar, bar_mma = sBar + 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x % a.H, b = blockIdx.x / a.H;
@@ -216,23 +219,25 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     mbar_init(bar_tma, 1); mbar_init(bar_mma, 1);
     fence_barrier_init(); fence_proxy_async();
   }
-  if (warp == 0) tmem_alloc(sBar + 32, 512);
+  if (warp == 0) tmem_alloc(sBar + 32, 256);
   for (int j = tid; j < 128; j += A_THREADS) kb[j] = (j < S) ? a.key_bias[(int64_t)b * S + j] : -INFINITY;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tslot;
-  // TMEM columns: S [0,128) | dP [128,256) | dV [256,320) | dK [320,384) | dQ [384,448)
-  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
+  // TMEM columns: S [0,128) | dP [128,256)   then   dV [0,64) | dK [64,128) | dQ [128,192)
+  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem, tdK = tmem + 64, tdQ = tmem + 128;
 
   if (tid == 0) {
-    mbar_expect_tx(bar_tma, 4 * T16);
+    mbar_expect_tx(bar_tma, 4 * TN);
     tma_load_2d(sQ, &tm_q, bar_tma, h * ADH, b * S);
     tma_load_2d(sK, &tm_q, bar_tma, a.H * ADH + h * ADH, b * S);
     tma_load_2d(sV, &tm_q, bar_tma, 2 * a.H * ADH + h * ADH, b * S);
     tma_load_2d(sdO, &tm_do, bar_tma, h * ADH, b * S);
     mbar_wait(bar_tma, 0);
     tcgen05_fence_after();
+    // M = 128 rows are read from the NP-row Q / dO tiles: rows NP..127 alias the following tiles and only
+    // produce accumulator rows that are never used
     const uint32_t idesc = make_idesc_mn(128, NP, false, false);
 #pragma unroll
     for (int k = 0; k < ADH / 16; ++k) {
@@ -269,6 +274,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t lane_off = ((uint32_t)(warp * 32) << 16);
     const uint64_t drow = (((uint64_t)b * a.H + h) * S + (valid ? row : 0)) * (uint64_t)S;
     const float scale = a.scale;
+    const bool in_tile = row < NP;                  // the P / dS buffers only have NP rows
     for (int c = 0; c < NP; c += 16) {
       float sv[16], dv[16];
       tmem_ld16_nowait(tS + lane_off + c, sv);
@@ -280,7 +286,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int col = c + j;
         float p = 0.f, ds = 0.f;
         if (valid && col < S) {
-          p = expf(sv[j] * scale + kb[col] - lse_i);
+          p = __expf(sv[j] * scale + kb[col] - lse_i);
           float dp = dv[j];
           float pd = p;
           if (a.drop.on) {
@@ -295,15 +301,19 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const uint32_t db = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(ds));
         if (j & 1) { pp[j >> 1] |= pb << 16; dd[j >> 1] |= db << 16; } else { pp[j >> 1] = pb; dd[j >> 1] = db; }
       }
-      const int kblk = c >> 6, cc = c & 63;
-      *reinterpret_cast<uint4*>(gP + kblk * T16 + sw_off(row, cc)) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
-      *reinterpret_cast<uint4*>(gP + kblk * T16 + sw_off(row, cc + 8)) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
-      *reinterpret_cast<uint4*>(gdS + kblk * T16 + sw_off(row, cc)) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
-      *reinterpret_cast<uint4*>(gdS + kblk * T16 + sw_off(row, cc + 8)) = make_uint4(dd[4], dd[5], dd[6], dd[7]);
+      if (in_tile) {
+        const int kblk = c >> 6, cc = c & 63;
+        *reinterpret_cast<uint4*>(gP + kblk * TN + sw_off(row, cc)) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+        *reinterpret_cast<uint4*>(gP + kblk * TN + sw_off(row, cc + 8)) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
+        *reinterpret_cast<uint4*>(gdS + kblk * TN + sw_off(row, cc)) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+        *reinterpret_cast<uint4*>(gdS + kblk * TN + sw_off(row, cc + 8)) = make_uint4(dd[4], dd[5], dd[6], dd[7]);
+      }
     }
-    for (int c = NP; c < 128; c += 8) {             // zero the unused key columns (read as M rows below)
-      *reinterpret_cast<uint4*>(gP + (c >> 6) * T16 + sw_off(row, c & 63)) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(gdS + (c >> 6) * T16 + sw_off(row, c & 63)) = make_uint4(0, 0, 0, 0);
+    if (in_tile) {
+      for (int c = NP; c < 128; c += 8) {           // zero the unused key columns (read as M rows below)
+        *reinterpret_cast<uint4*>(gP + (c >> 6) * TN + sw_off(row, c & 63)) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(gdS + (c >> 6) * TN + sw_off(row, c & 63)) = make_uint4(0, 0, 0, 0);
+      }
     }
   }
   fence_proxy_async();
@@ -311,19 +321,18 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   __syncthreads();
   if (tid == 0) {
     tcgen05_fence_after();
-    // dV[j,d] = sum_i P[i,j] dO[i,d]   A = P^T (MN-major over the [i][j] buffer), B = dO (MN-major), K = i (128)
+    // dV[j,d] = sum_i P[i,j] dO[i,d]   A = P^T (MN-major over the [i][j] buffer), B = dO (MN-major), K = i (NP)
     // dK[j,d] = sum_i dS[i,j] Q[i,d]   A = dS^T (MN-major),                      B = Q  (MN-major)
     const uint32_t id_t = make_idesc_mn(128, ADH, true, true);
-#pragma unroll
-    for (int k = 0; k < QT / 16; ++k) {
-      // MN-major A: 64-wide M blocks (j) are the two [128][64] sub-tiles (LBO = 16 KiB); 8-row k groups 1024 B apart
-      umma_bf16(tdV, umma_desc(sP + k * 2048, T16, 1024), umma_desc(sdO + k * 2048, 8192, 1024), id_t, k > 0);
-      umma_bf16(tdK, umma_desc(sdS + k * 2048, T16, 1024), umma_desc(sQ + k * 2048, 8192, 1024), id_t, k > 0);
+    for (int k = 0; k < NP / 16; ++k) {
+      // MN-major A: 64-wide M blocks (j) are the two [NP][64] sub-tiles (LBO = TN); 8-row k groups 1024 B apart
+      umma_bf16(tdV, umma_desc(sP + k * 2048, TN, 1024), umma_desc(sdO + k * 2048, 8192, 1024), id_t, k > 0);
+      umma_bf16(tdK, umma_desc(sdS + k * 2048, TN, 1024), umma_desc(sQ + k * 2048, 8192, 1024), id_t, k > 0);
     }
     // dQ[i,d] = sum_j dS[i,j] K[j,d]   A = dS (K-major), B = K (MN-major), K = j (NP)
     const uint32_t id_q = make_idesc_mn(128, ADH, false, true);
     for (int k = 0; k < NP / 16; ++k)
-      umma_bf16(tdQ, umma_desc(sdS + (k >> 2) * T16 + (k & 3) * 32, 16, 1024), umma_desc(sK + k * 2048, 8192, 1024), id_q, k > 0);
+      umma_bf16(tdQ, umma_desc(sdS + (k >> 2) * TN + (k & 3) * 32, 16, 1024), umma_desc(sK + k * 2048, 8192, 1024), id_q, k > 0);
     umma_commit(bar_mma);
   }
   mbar_wait(bar_mma, 1);
@@ -360,11 +369,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 0) { __syncwarp(); tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
+  if (warp == 0) { __syncwarp(); tcgen05_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 static constexpr int FWD_SMEM = QT * 128 + 2 * 160 * 128 + 3 * QT * 128 + 64 + 160 * 4 + 1024 + 256;
-static constexpr int BWD_SMEM = 8 * QT * 128 + 64 + 128 * 4 + 1024 + 256;
+static int bwd_smem_bytes(int NP) { return 1024 /*align*/ + 1024 /*barriers, key bias*/ + 8 * NP * 128 + 16384 /*read slack*/; }
 
 int attention_tc_fwd(const clgAttentionFwdParams& p, cudaStream_t stream) {
   if (p.dtype != CLG_BF16 || p.S > 160 || p.S < 1) return CLG_ERR_UNSUPPORTED;
@@ -393,14 +402,15 @@ int attention_tc_bwd(const clgAttentionBwdParams& p, cudaStream_t stream) {
   if (p.dtype != CLG_BF16 || p.S > 128 || p.S < 1) return CLG_ERR_UNSUPPORTED;
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
-  std::call_once(once, [] { err = cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM); });
+  std::call_once(once, [] { err = cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes(128)); });
   CLG_CUDA_OK(err, "cudaFuncSetAttribute(attn_tc_bwd)");
   const int NP = (p.S + 15) / 16 * 16;
+  const int BWD_SMEM = bwd_smem_bytes(NP);
   CUtensorMap tq, tdo;
   const int64_t rows = (int64_t)p.B * p.S;
-  int st = make_tmap_bf16(&tq, p.qkv, 3LL * p.H * ADH, rows, p.ld_qkv, QT);
+  int st = make_tmap_bf16(&tq, p.qkv, 3LL * p.H * ADH, rows, p.ld_qkv, NP);
   if (st != CLG_OK) return st;
-  st = make_tmap_bf16(&tdo, p.dctx, (int64_t)p.H * ADH, rows, p.ld_dctx, QT);
+  st = make_tmap_bf16(&tdo, p.dctx, (int64_t)p.H * ADH, rows, p.ld_dctx, NP);
   if (st != CLG_OK) return st;
   AttnTcArgs a;
   memset(&a, 0, sizeof(a));

@@ -95,6 +95,22 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return cdf + x * pdf;
 }
 
+// gelu(u) and gelu'(u) together from ONE exponential: erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7,
+// branch-free), whose e^{-x^2} with x = u/sqrt(2) is also the Gaussian of gelu'(u) = Phi(u) + u phi(u).
+__device__ __forceinline__ void gelu_pair_fast(float u, float& g, float& dg) {
+  const float x = u * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, fabsf(x), 1.0f));
+  const float E = __expf(-x * x);
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfv = copysignf(1.0f - poly * t * E, x);
+  const float cdf = fmaf(0.5f, erfv, 0.5f);
+  g = u * cdf;
+  dg = fmaf(u * E, 0.39894228040143267794f, cdf);
+}
+
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }

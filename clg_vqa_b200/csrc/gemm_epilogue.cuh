@@ -47,6 +47,11 @@ __device__ __forceinline__ float epi_scalar(const EpiArgs& e, int row, int col, 
       if (e.aux_out) store_from_f32(e.aux_out, e.aux_out_dtype, (int64_t)row * e.ld_aux_out + col, v);
       v = gelu_erf(v);
       break;
+    case CLG_ACT_GELU_GRAD:
+      if (e.aux_out) store_from_f32(e.aux_out, e.aux_out_dtype, (int64_t)row * e.ld_aux_out + col, dgelu_erf(v));
+      v = gelu_erf(v);
+      break;
+    case CLG_ACT_MUL_AUX: v *= load_as_f32(e.aux_in, e.aux_in_dtype, (int64_t)row * e.ld_aux_in + col); break;
     case CLG_ACT_RELU: v = fmaxf(v, 0.f); break;
     case CLG_ACT_TANH: v = tanhf(v); break;
     case CLG_ACT_DGELU: v *= dgelu_erf(load_as_f32(e.aux_in, e.aux_in_dtype, (int64_t)row * e.ld_aux_in + col)); break;

@@ -10,7 +10,7 @@
 // transposes in memory.  Optional split-K (atomic fp32 accumulate) for the wgrad shapes whose output
 // has too few tiles to fill 148 SMs.
 #include <mutex>
-#include "gemm_epilogue.cuh"
+#include "gemm_epilogue_tc.cuh"
 #include "tc_common.cuh"
 
 namespace clg {
@@ -18,7 +18,7 @@ namespace clg {
 static constexpr int BM = 128;
 static constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
 static constexpr int UMMA_K = 16;
-static constexpr int NUM_THREADS = 192;  // 6 warps
+static constexpr int NUM_THREADS = 320;  // 10 warps: TMA, MMA, 8 epilogue
 static constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KiB
 
 template <int BN> struct TileCfg {
@@ -26,7 +26,8 @@ template <int BN> struct TileCfg {
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int KSTAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;          // power of two >= 32 for BN in {64,128,256}
-  static constexpr int SMEM_BYTES = KSTAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = KSTAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                    8 * STG_FLOATS * 4 /*epilogue staging, one [32][33] fp32 tile per warp*/;
 };
 
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) { return make_idesc_mn(BM, n, a_mn, b_mn); }
@@ -34,6 +35,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
 struct TcArgs {
   int M, N, K;
   int num_m, num_n, splits, kper, kblocks;
+  int staged;      // epilogue may use the coalesced shared-memory staged path
 };
 
 template <int BN, bool A_K, bool B_K>
@@ -62,7 +64,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
     for (int s = 0; s < KSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -146,7 +148,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else {
+    // 8 epilogue warps: two per TMEM lane quarter, interleaved over the 32-column chunks of the tile
     const int q = warp & 3;                // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;      // 0: warps 2-5, 1: warps 6-9
+    float* stg = reinterpret_cast<float*>(smem_gen + KSTAGES * Cfg::STAGE_BYTES + 256) + (warp - 2) * STG_FLOATS;
     int local = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++local) {
       const int tile = w / t.splits;
@@ -154,14 +159,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       mbar_wait(tfull_bar(as), aphase);
+      __syncwarp();
       tcgen05_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
+      const int r0 = m_blk * BM + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         float v[32];
         tmem_ld32(taddr + (uint32_t)(c * 32), v);
-        epi_row_chunk<32>(e, row, n_blk * BN + c * 32, v);
+        tc_epi_chunk(e, stg, r0, n_blk * BN + c * 32, lane, t.staged != 0, v);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -270,6 +276,7 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
     }
     e.accumulate = 2;
   }
+  t.staged = (epi_can_stage(e) && (p.N % 2 == 0)) ? 1 : 0;
   const int total = t.num_m * t.num_n * t.splits;
   const int grid = total < sms ? total : sms;
   gemm_tc_kernel<BN, A_K, B_K><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, t, e);

@@ -541,7 +541,10 @@ class Engine:
         ops.gemm(lw["ctx"], self._w(omod, d, d), lw["y1"], bias=self._bias(omod, d), residual=x, dropout=site_o)
         ops.layernorm_fwd(lw["y1"], ln1.weight.data, ln1.bias.data, eps, y=lw["x1"], y_lowp=lw["x1_lp"] if bf else None,
                           mean=lw["m1"], rstd=lw["r1"])
-        ops.gemm(lw["x1_lp"], self._w(f1mod, F, d), lw["h"], bias=self._bias(f1mod, F), act=ops.ACT_GELU, aux_out=lw["u"])
+        # bf16 mode saves gelu'(u) (one shared exponential in the epilogue) so the backward epilogue is a multiply;
+        # the fp32 correctness mode saves u and evaluates the exact erf / exp derivative in the backward
+        ops.gemm(lw["x1_lp"], self._w(f1mod, F, d), lw["h"], bias=self._bias(f1mod, F),
+                 act=ops.ACT_GELU_GRAD if bf else ops.ACT_GELU, aux_out=lw["u"])
         ops.gemm(lw["h"], self._w(f2mod, d, F), lw["y2"], bias=self._bias(f2mod, d), residual=lw["x1"], dropout=site_f)
         ops.layernorm_fwd(lw["y2"], ln2.weight.data, ln2.bias.data, eps, y=lw["x2"], y_lowp=lw["x2_lp"] if bf else None,
                           mean=lw["m2"], rstd=lw["r2"], row_valid=row_valid, valid_post=row_valid is not None)
@@ -643,7 +646,8 @@ class Engine:
                           dbias=self._gvec(self.b_slot[id(f2mod)], d), dropout_in=site_f,
                           row_valid=row_valid, valid_post=row_valid is not None)
         self._wgrad(dgo, lw["h"], f2mod, d, F)
-        ops.gemm(dgo, self._w(f2mod, d, F), ws["du"], b_kmajor=False, act=ops.ACT_DGELU, aux_in=lw["u"])
+        ops.gemm(dgo, self._w(f2mod, d, F), ws["du"], b_kmajor=False,
+                 act=ops.ACT_MUL_AUX if ws["lp"] == torch.bfloat16 else ops.ACT_DGELU, aux_in=lw["u"])
         ops.colsum(ws["du"], self._gvec(self.b_slot[id(f1mod)], F))
         self._wgrad(ws["du"], lw["x1_lp"], f1mod, F, d)
         ops.gemm(ws["du"], self._w(f1mod, F, d), dx, b_kmajor=False, residual=dy)

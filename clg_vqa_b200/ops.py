@@ -9,7 +9,7 @@ from typing import Optional
 import torch
 
 from . import _lib as L
-from ._lib import (ACT_DGELU, ACT_DRELU, ACT_DTANH, ACT_GELU, ACT_NONE, ACT_RELU, ACT_TANH,  # noqa: F401
+from ._lib import (ACT_DGELU, ACT_DRELU, ACT_DTANH, ACT_GELU, ACT_GELU_GRAD, ACT_MUL_AUX, ACT_NONE, ACT_RELU, ACT_TANH,  # noqa: F401
                    CLG_BF16, CLG_F32, GEMM_AUTO, GEMM_SIMT, GEMM_TC, ClgError)
 
 _launches = 0   # number of C-ABI kernel entry calls (bench.py reports it as gpu_launches)

@@ -82,7 +82,10 @@ typedef enum {
   CLG_ACT_TANH = 3,   /* M3P BertPooler (m3p_transformer.py:L554-560) */
   CLG_ACT_DGELU = 4,  /* v *= gelu'(aux_in)            aux_in = saved pre-activation */
   CLG_ACT_DRELU = 5,  /* v *= (aux_in > 0)             aux_in = saved activation output */
-  CLG_ACT_DTANH = 6   /* v *= 1 - aux_in^2             aux_in = saved activation output */
+  CLG_ACT_DTANH = 6,  /* v *= 1 - aux_in^2             aux_in = saved activation output */
+  CLG_ACT_GELU_GRAD = 7, /* erf GeLU; aux_out receives gelu'(pre-activation) instead of the pre-activation, so the
+                            backward GEMM epilogue is a plain multiply (CLG_ACT_MUL_AUX) */
+  CLG_ACT_MUL_AUX = 8 /* v *= aux_in */
 } clgAct;
 
 typedef enum { CLG_GEMM_AUTO = 0, CLG_GEMM_TC = 1, CLG_GEMM_SIMT = 2 } clgGemmBackend;
