@@ -108,7 +108,8 @@ def cpu_reference_step_rate(B=8, R=36, steps=2, warmup=1, layers=12, with_optimi
     model = BertForVLTasks(cfg, C.gqa_task_cfg(R), ["TASK15"])
     sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()
           if S.canonical_key(k) == k}
-    full = lambda: {k: sd[S.canonical_key(k)] for k in model.state_dict().keys()}   # noqa: E731
+    all_keys = list(model.state_dict().keys())
+    full = lambda: {k: sd[S.canonical_key(k)] for k in all_keys}   # noqa: E731
     del model
     b = S.synth_batch(B, num_regions=R, seed=1234)
     st = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in sd.items()} if with_optimizer else None
@@ -172,6 +173,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line
         dist.init_process_group(backend="nccl", device_id=dev)
     ops.device_check(local_rank)
 
