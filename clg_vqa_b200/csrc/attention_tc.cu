@@ -59,22 +59,30 @@ __device__ __forceinline__ void for_each_score(uint32_t taddr, int NP, F&& f) {
 
 // ------------------------------------------------------------------------------------------------
 // forward
+// Shared memory: [barriers | Q (QR rows) | K (NP) | V (NP) | P (KB blocks of QR rows)] + 16 KiB read slack,
+// QR = NP when the whole sequence fits one query tile (rows NP..127 of the M = 128 MMAs then alias the
+// following tiles and only produce accumulator rows that are never used), else 128.
+// TMEM: S in columns [0, NP); O reuses columns [0, 64) once P has been written to shared memory.
+// NCH > 0: the NP = 16*NCH exponentials of a row stay in registers between the sum pass and the P pass.
 // ------------------------------------------------------------------------------------------------
+template <int NCH>
 __global__ void __launch_bounds__(A_THREADS)
-attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const AttnTcArgs a) {
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const AttnTcArgs a,
+                   const int QR, const uint32_t tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const int NP = a.NP;
   const int KB = (NP + 63) / 64;                    // 64-wide key blocks of the P tile
-  const uint32_t sQ = base;                         // [128][64]
-  const uint32_t sK = sQ + QT * 128;                // [NP][64]   (NP rounded to 8-row groups)
-  const uint32_t sV = sK + 160 * 128;               // [NP][64]
-  const uint32_t sP = sV + 160 * 128;               // KB x [128][64]
-  const uint32_t sBar = sP + 3 * QT * 128;          // barriers + tmem slot + key bias
+  const uint32_t TQ = (uint32_t)QR * 128u, TN = (uint32_t)NP * 128u;
+  const uint32_t sBar = base;
+  const uint32_t sQ = base + 1024;
+  const uint32_t sK = sQ + TQ;
+  const uint32_t sV = sK + TN;
+  const uint32_t sP = sV + TN;                      // KB x [QR][64]
   uint8_t* gP = gen + (sP - base);
-  float* kb = reinterpret_cast<float*>(gen + (sBar - base) + 64);
-  volatile uint32_t* tslot = reinterpret_cast<volatile uint32_t*>(gen + (sBar - base) + 32);
+  float* kb = reinterpret_cast<float*>(gen + 64);
+  volatile uint32_t* tslot = reinterpret_cast<volatile uint32_t*>(gen + 32);
   const uint32_t bar_tma = sBar, bar_mma = sBar + 8;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -88,16 +96,16 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     mbar_init(bar_tma, 1); mbar_init(bar_mma, 1);
     fence_barrier_init(); fence_proxy_async();
   }
-  if (warp == 0) tmem_alloc(sBar + 32, 256);
+  if (warp == 0) tmem_alloc(sBar + 32, tmem_cols);
   for (int j = tid; j < NP; j += A_THREADS) kb[j] = (j < S) ? a.key_bias[(int64_t)b * S + j] : -INFINITY;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tslot;
-  const uint32_t tS = tmem, tO = tmem + 192;
+  const uint32_t tS = tmem, tO = tmem;
 
   if (tid == 0) {
-    mbar_expect_tx(bar_tma, (uint32_t)(QT * 128 + 2 * NP * 128));
+    mbar_expect_tx(bar_tma, TQ + 2 * TN);
     tma_load_2d(sQ, &tm_q, bar_tma, h * ADH, b * S + qt * QT);
     tma_load_2d(sK, &tm_kv, bar_tma, a.H * ADH + h * ADH, b * S);
     tma_load_2d(sV, &tm_kv, bar_tma, 2 * a.H * ADH + h * ADH, b * S);
@@ -117,35 +125,46 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int qi = qt * QT + row;                     // query index inside the sample
   const uint32_t trow = tS + ((uint32_t)(warp * 32) << 16);
   const float scale = a.scale;
-  float m = -INFINITY;
-  for_each_score(trow, NP, [&](int j, float s) { m = fmaxf(m, s * scale + kb[j]); });
-  float sum = 0.f;
-  for_each_score(trow, NP, [&](int j, float s) { sum += expf(s * scale + kb[j] - m); });
-  const float inv = 1.0f / sum;
   const bool valid = qi < S;
+  const bool in_tile = row < QR;
+  const bool warp_live = (qt * QT + warp * 32) < S; // warp-uniform: any valid row in this warp
   const uint64_t drow = (((uint64_t)b * a.H + h) * S + (valid ? qi : 0)) * (uint64_t)S;
-  {
-    // normalised probabilities -> dropout -> bf16 -> swizzled smem (8 values = one 16 B chunk at a time)
-    int c = 0;
-    uint32_t pk[4];
-    auto emit = [&](int j, float s) {
-      float p = valid ? expf(s * scale + kb[j] - m) * inv : 0.f;
-      if (a.drop.on && j < S) p = drop_apply(a.drop, drow + j, p);
-      const int e = j & 7;
-      const uint32_t hbits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(p));
-      if (e & 1) pk[e >> 1] |= hbits << 16; else pk[e >> 1] = hbits;
-      if (e == 7) {
-        const int kblk = j >> 6;
-        *reinterpret_cast<uint4*>(gP + kblk * (QT * 128) + sw_off(row, (j & 63) - 7)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  float m = -INFINITY, sum = 0.f;
+  uint32_t pk[4];
+  auto emit = [&](int j, float p) {                  // 8 consecutive probabilities -> one swizzled 16 B chunk
+    if (a.drop.on && j < S) p = drop_apply(a.drop, drow + j, p);
+    const int e = j & 7;
+    const uint32_t hbits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(p));
+    if (e & 1) pk[e >> 1] |= hbits << 16; else pk[e >> 1] = hbits;
+    if (e == 7 && in_tile)
+      *reinterpret_cast<uint4*>(gP + (j >> 6) * TQ + sw_off(row, (j & 63) - 7)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  };
+  if (warp_live) {
+    if (NCH > 0) {
+      float ex[NCH > 0 ? NCH * 16 : 1];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        tmem_ld16(trow + c * 16, &ex[c * 16]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { ex[c * 16 + j] = ex[c * 16 + j] * scale + kb[c * 16 + j]; m = fmaxf(m, ex[c * 16 + j]); }
       }
-    };
-    (void)c;
-    for_each_score(trow, NP, emit);
-    // zero the tail of the last 64-block so the K-steps that straddle it read zeros, not stale smem
-    for (int j = NP; j < KB * 64; j += 8)
-      *reinterpret_cast<uint4*>(gP + (j >> 6) * (QT * 128) + sw_off(row, j & 63)) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int j = 0; j < NCH * 16; ++j) { ex[j] = __expf(ex[j] - m); sum += ex[j]; }
+      const float inv = valid ? 1.0f / sum : 0.f;
+#pragma unroll
+      for (int j = 0; j < NCH * 16; ++j) emit(j, ex[j] * inv);
+    } else {
+      for_each_score(trow, NP, [&](int j, float s) { m = fmaxf(m, s * scale + kb[j]); });
+      for_each_score(trow, NP, [&](int j, float s) { sum += __expf(s * scale + kb[j] - m); });
+      const float inv = valid ? 1.0f / sum : 0.f;
+      for_each_score(trow, NP, [&](int j, float s) { emit(j, __expf(s * scale + kb[j] - m) * inv); });
+    }
+    if (valid && a.lse) a.lse[((int64_t)b * a.H + h) * S + qi] = m + __logf(sum);
+  } else if (in_tile) {
+    for (int j = 0; j < NP; j += 8)
+      *reinterpret_cast<uint4*>(gP + (j >> 6) * TQ + sw_off(row, j & 63)) = make_uint4(0, 0, 0, 0);
   }
-  if (valid && a.lse && lane >= 0) a.lse[((int64_t)b * a.H + h) * S + qi] = m + logf(sum);
+  (void)KB;
   fence_proxy_async();
   tcgen05_fence_before();
   __syncthreads();
@@ -154,7 +173,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t idesc = make_idesc_mn(128, ADH, false, true);
     const int ksteps = NP / 16;
     for (int k = 0; k < ksteps; ++k) {
-      const uint32_t pa = sP + (k >> 2) * (QT * 128) + (k & 3) * 32;
+      const uint32_t pa = sP + (k >> 2) * TQ + (k & 3) * 32;
       umma_bf16(tO, umma_desc(pa, 16, 1024), umma_desc(sV + k * 2048, 8192, 1024), idesc, k > 0);
     }
     umma_commit(bar_mma);
@@ -162,7 +181,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   mbar_wait(bar_mma, 1);
   __syncwarp();
   tcgen05_fence_after();
-  {
+  if (warp_live) {
     float o[32];
     bf16* og = a.ctx + ((int64_t)b * S + qi) * a.ld_ctx + h * ADH;
 #pragma unroll
@@ -185,7 +204,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 0) { __syncwarp(); tcgen05_fence_after(); tmem_dealloc(tmem, 256); }
+  if (warp == 0) { __syncwarp(); tcgen05_fence_after(); tmem_dealloc(tmem, tmem_cols); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -372,30 +391,53 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 0) { __syncwarp(); tcgen05_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
-static constexpr int FWD_SMEM = QT * 128 + 2 * 160 * 128 + 3 * QT * 128 + 64 + 160 * 4 + 1024 + 256;
+static int fwd_smem_bytes(int QR, int NP) {
+  const int KB = (NP + 63) / 64;
+  return 1024 /*align*/ + 1024 /*barriers, key bias*/ + QR * 128 + 2 * NP * 128 + KB * QR * 128 + 16384 /*read slack*/;
+}
 static int bwd_smem_bytes(int NP) { return 1024 /*align*/ + 1024 /*barriers, key bias*/ + 8 * NP * 128 + 16384 /*read slack*/; }
+
+template <int NCH>
+static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnTcArgs& a, int QR, uint32_t tmem_cols, int grid,
+                           cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    err = cudaFuncSetAttribute(attn_tc_fwd_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem_bytes(128, 160));
+  });
+  CLG_CUDA_OK(err, "cudaFuncSetAttribute(attn_tc_fwd)");
+  attn_tc_fwd_kernel<NCH><<<grid, A_THREADS, fwd_smem_bytes(QR, a.NP), stream>>>(tq, tkv, a, QR, tmem_cols);
+  return check_launch("attn_tc_fwd_kernel");
+}
 
 int attention_tc_fwd(const clgAttentionFwdParams& p, cudaStream_t stream) {
   if (p.dtype != CLG_BF16 || p.S > 160 || p.S < 1) return CLG_ERR_UNSUPPORTED;
-  static std::once_flag once;
-  static cudaError_t err = cudaSuccess;
-  std::call_once(once, [] { err = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM); });
-  CLG_CUDA_OK(err, "cudaFuncSetAttribute(attn_tc_fwd)");
   const int NP = (p.S + 15) / 16 * 16;
+  const int n_qt = (p.S + QT - 1) / QT;
+  const int QR = (n_qt == 1) ? NP : QT;
   CUtensorMap tq, tkv;
   const int64_t rows = (int64_t)p.B * p.S, cols = 3LL * p.H * ADH;
-  int st = make_tmap_bf16(&tq, p.qkv, cols, rows, p.ld_qkv, QT);
+  int st = make_tmap_bf16(&tq, p.qkv, cols, rows, p.ld_qkv, QR);
   if (st != CLG_OK) return st;
   st = make_tmap_bf16(&tkv, p.qkv, cols, rows, p.ld_qkv, NP);
   if (st != CLG_OK) return st;
   AttnTcArgs a;
   memset(&a, 0, sizeof(a));
-  a.B = p.B; a.S = p.S; a.H = p.H; a.NP = NP; a.n_qt = (p.S + QT - 1) / QT;
+  a.B = p.B; a.S = p.S; a.H = p.H; a.NP = NP; a.n_qt = n_qt;
   a.scale = p.scale; a.key_bias = p.key_bias; a.lse = p.lse;
   a.ctx = (bf16*)p.ctx; a.ld_ctx = p.ld_ctx;
   a.drop = make_drop(p.dropout);
-  attn_tc_fwd_kernel<<<p.B * p.H * a.n_qt, A_THREADS, FWD_SMEM, stream>>>(tq, tkv, a);
-  return check_launch("attn_tc_fwd_kernel");
+  const uint32_t tmem_cols = NP <= 64 ? 64 : (NP <= 128 ? 128 : 256);
+  const int grid = p.B * p.H * n_qt;
+  switch (NP / 16) {
+    case 1: return launch_attn_fwd<1>(tq, tkv, a, QR, tmem_cols, grid, stream);
+    case 2: return launch_attn_fwd<2>(tq, tkv, a, QR, tmem_cols, grid, stream);
+    case 3: return launch_attn_fwd<3>(tq, tkv, a, QR, tmem_cols, grid, stream);
+    case 4: return launch_attn_fwd<4>(tq, tkv, a, QR, tmem_cols, grid, stream);
+    case 5: return launch_attn_fwd<5>(tq, tkv, a, QR, tmem_cols, grid, stream);
+    case 6: return launch_attn_fwd<6>(tq, tkv, a, QR, tmem_cols, grid, stream);
+    default: return launch_attn_fwd<0>(tq, tkv, a, QR, tmem_cols, grid, stream);
+  }
 }
 
 int attention_tc_bwd(const clgAttentionBwdParams& p, cudaStream_t stream) {

@@ -10,6 +10,7 @@
 // transposes in memory.  Optional split-K (atomic fp32 accumulate) for the wgrad shapes whose output
 // has too few tiles to fill 148 SMs.
 #include <mutex>
+#include <stdlib.h>
 #include "gemm_epilogue_tc.cuh"
 #include "tc_common.cuh"
 
@@ -36,9 +37,13 @@ struct TcArgs {
   int M, N, K;
   int num_m, num_n, splits, kper, kblocks;
   int staged;      // epilogue may use the coalesced shared-memory staged path
+  int total_units; // work units: (m block | pair of m blocks when MC) x n block x split
 };
 
-template <int BN, bool A_K, bool B_K>
+// MC: clusters of two CTAs work on two vertically adjacent 128-row tiles of the same N block; each CTA loads
+// half of the shared B tile and TMA-multicasts it into both CTAs' shared memory (A 16 KiB + B/2 per k-block from
+// L2 instead of A + B), so the L2 -> SM traffic of the weight / activation tile is halved.
+template <int BN, bool A_K, bool B_K, bool MC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const TcArgs t, const EpiArgs e) {
@@ -63,7 +68,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
-    for (int s = 0; s < KSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < KSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), MC ? 2 : 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -74,18 +79,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();          // the peer's barriers must be initialised before any multicast arrives
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  const int total_work = t.num_m * t.num_n * t.splits;
+  const int crank = MC ? (int)cluster_ctarank() : 0;
+  const int total_work = t.total_units;
+  const int w_first = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int w_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto m_block_of = [&](int tile) { const int mi = tile / t.num_n; return MC ? 2 * mi + crank : mi; };
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = w_first; w < total_work; w += w_step) {
         const int split = w % t.splits;
         const int tile = w / t.splits;
-        const int n_blk = tile % t.num_n, m_blk = tile / t.num_n;
+        const int n_blk = tile % t.num_n, m_blk = m_block_of(tile);
         const int kb0 = split * t.kper;
         const int kb1 = min(t.kblocks, kb0 + t.kper);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -100,7 +110,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             for (int j = 0; j < BM / 64; ++j)
               tma_load_2d(sa + j * (64 * BK * 2), &tma_a, full_bar(stage), m_blk * BM + j * 64, kb * BK);
           }
-          if (B_K) {
+          if (MC) {
+            // this CTA fetches its half of the B tile and multicasts it to both CTAs of the pair
+            if (B_K) {
+              tma_load_2d_mc(sb + crank * (BN / 2) * 128, &tma_b, full_bar(stage), kb * BK, n_blk * BN + crank * (BN / 2), 3);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j) {
+                const int jj = crank * (BN / 128) + j;
+                tma_load_2d_mc(sb + jj * (64 * BK * 2), &tma_b, full_bar(stage), n_blk * BN + jj * 64, kb * BK, 3);
+              }
+            }
+          } else if (B_K) {
             tma_load_2d(sb, &tma_b, full_bar(stage), kb * BK, n_blk * BN);
           } else {
 #pragma unroll
@@ -116,7 +137,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       constexpr uint32_t idesc = make_idesc(BN, !A_K, !B_K);
       int stage = 0; uint32_t phase = 0;
       int local = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++local) {
+      for (int w = w_first; w < total_work; w += w_step, ++local) {
         const int split = w % t.splits;
         const int kb0 = split * t.kper;
         const int kb1 = min(t.kblocks, kb0 + t.kper);
@@ -141,7 +162,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                        : umma_desc(sb + k * (UMMA_K * 128), 64 * BK * 2, 1024);
             umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
+          // frees the smem slot once these MMAs have read it (in both CTAs of a multicast pair: the peer's
+          // next TMA writes into this CTA's slot as well)
+          if (MC) umma_commit_mc(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
           if (++stage == KSTAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(as));        // accumulator complete -> epilogue
@@ -153,9 +176,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int half = (warp - 2) >> 2;      // 0: warps 2-5, 1: warps 6-9
     float* stg = reinterpret_cast<float*>(smem_gen + KSTAGES * Cfg::STAGE_BYTES + 256) + (warp - 2) * STG_FLOATS;
     int local = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++local) {
+    for (int w = w_first; w < total_work; w += w_step, ++local) {
       const int tile = w / t.splits;
-      const int n_blk = tile % t.num_n, m_blk = tile / t.num_n;
+      const int n_blk = tile % t.num_n, m_blk = m_block_of(tile);
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       mbar_wait(tfull_bar(as), aphase);
@@ -177,6 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   tcgen05_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();          // the peer may still multicast into / arrive on this CTA's shared memory
   if (warp == 1) {
     __syncwarp();
     tcgen05_fence_after();
@@ -220,13 +244,19 @@ int make_tmap_bf16(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer
   return CLG_OK;
 }
 
-template <int BN, bool A_K, bool B_K>
+static bool multicast_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("CLG_GEMM_MC"); v = (s && s[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+template <int BN, bool A_K, bool B_K, bool MC>
 static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, A_K, B_K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, A_K, B_K, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::SMEM_BYTES);
   });
   CLG_CUDA_OK(attr_err, "cudaFuncSetAttribute(gemm_tc)");
@@ -236,7 +266,7 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
   if (A_K) st = make_tmap_bf16(&ta, p.A, p.K, p.M, p.lda, BM);
   else     st = make_tmap_bf16(&ta, p.A, p.M, p.K, p.lda, BK);
   if (st != CLG_OK) return st;
-  if (B_K) st = make_tmap_bf16(&tb, p.B, p.K, p.N, p.ldb, BN);
+  if (B_K) st = make_tmap_bf16(&tb, p.B, p.K, p.N, p.ldb, MC ? BN / 2 : BN);
   else     st = make_tmap_bf16(&tb, p.B, p.N, p.K, p.ldb, BK);
   if (st != CLG_OK) return st;
 
@@ -251,7 +281,7 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
                           p.c_dtype == CLG_F32 && !p.dropout.p);
   if (splits <= 0) {
     splits = 1;
-    const int tiles = t.num_m * t.num_n;
+    const int tiles = (MC ? 2 * ((t.num_m + 1) / 2) : t.num_m) * t.num_n;
     if (can_split && tiles < sms && t.kblocks >= 16) {
       // pick the split count that best fills whole waves of SMs, >= 8 k-blocks (K = 512) per split
       const int max_s = t.kblocks / 8 < 32 ? t.kblocks / 8 : 32;
@@ -277,18 +307,42 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
     e.accumulate = 2;
   }
   t.staged = (epi_can_stage(e) && (p.N % 2 == 0)) ? 1 : 0;
-  const int total = t.num_m * t.num_n * t.splits;
-  const int grid = total < sms ? total : sms;
-  gemm_tc_kernel<BN, A_K, B_K><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, t, e);
+  if (MC) {
+    t.total_units = ((t.num_m + 1) / 2) * t.num_n * t.splits;
+    const int max_clusters = sms / 2;
+    const int clusters = t.total_units < max_clusters ? t.total_units : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CLG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_K, B_K, MC>, ta, tb, t, e), "cudaLaunchKernelEx(gemm_tc, cluster 2)");
+    return check_launch("gemm_tc_kernel(mc)");
+  }
+  t.total_units = t.num_m * t.num_n * t.splits;
+  const int grid = t.total_units < sms ? t.total_units : sms;
+  gemm_tc_kernel<BN, A_K, B_K, MC><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, t, e);
   return check_launch("gemm_tc_kernel");
+}
+
+template <int BN, bool MC>
+static int dispatch_major2(const clgGemmParams& p, const EpiArgs& e, cudaStream_t s) {
+  if (p.a_kmajor && p.b_kmajor) return launch_tc<BN, true, true, MC>(p, e, s);
+  if (p.a_kmajor && !p.b_kmajor) return launch_tc<BN, true, false, MC>(p, e, s);
+  if (!p.a_kmajor && !p.b_kmajor) return launch_tc<BN, false, false, MC>(p, e, s);
+  return launch_tc<BN, false, true, MC>(p, e, s);
 }
 
 template <int BN>
 static int dispatch_major(const clgGemmParams& p, const EpiArgs& e, cudaStream_t s) {
-  if (p.a_kmajor && p.b_kmajor) return launch_tc<BN, true, true>(p, e, s);
-  if (p.a_kmajor && !p.b_kmajor) return launch_tc<BN, true, false>(p, e, s);
-  if (!p.a_kmajor && !p.b_kmajor) return launch_tc<BN, false, false>(p, e, s);
-  return launch_tc<BN, false, true>(p, e, s);
+  // pairs of vertically adjacent tiles share the B tile through TMA multicast whenever there are at least two
+  // row blocks (BN >= 128 so that each CTA's half of an MN-major B tile is a whole 64-wide box)
+  if (BN >= 128 && p.M > BM && multicast_enabled()) return dispatch_major2<(BN >= 128 ? BN : 128), true>(p, e, s);
+  return dispatch_major2<BN, false>(p, e, s);
 }
 
 // entry used by clg_gemm
