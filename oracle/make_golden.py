@@ -150,13 +150,59 @@ def make_case(ref, name, spec):
     print("%s: loss %.6f score %.4f  (%.1fs)" % (name, loss, score, time.time() - t0), flush=True)
 
 
+def make_sft_case(ref, name="uc2_L2_B4_sft", layers=2, vocab=4096, B=4, R=36, wseed=0, bseed=1234, density=0.59):
+    """SFT (train_task_sft.py:L409-461): pre-multiply the masked weights, install prune.CustomFromMask on the named
+    sub-modules of the UNMODIFIED reference model (what pruning_model_custom does at L122-132; its hard-coded
+    24-sub-layer loop is applied to this model's sub-layers), then the standard forward / loss / backward."""
+    import torch.nn.utils.prune as prune
+    from clg_vqa_b200 import sft
+    t0 = time.time()
+    task_cfg = C.gqa_task_cfg(max_region_num=R)
+    cfg, _ = ref_config(ref, "uc2", layers, vocab)
+    model = build_ref_model(ref, "uc2", cfg, task_cfg, wseed)
+    names = sft.uc2_masked_module_names(layers)
+    masks = sft.synth_mask_dict(model, names, density=density, seed=wseed)
+    model.load_state_dict(sft.premask_state_dict(model.state_dict(), masks))           # L432-453
+    mods = dict(model.named_modules())
+    for n in names:
+        prune.CustomFromMask.apply(mods[n], "weight", mask=masks[n + ".weight_mask"])  # L122-132
+    model.eval()
+    batch = batch_for("uc2", B, R, True, bseed, vocab)
+    logits, loss, score = run_reference(ref, model, cfg, task_cfg, batch, backward=True)
+    out = {"logits_fp32": logits.numpy(), "loss_fp32": np.float64(loss), "score_fp32": np.float64(score)}
+    gn, gv = [], []
+    seen = set()
+    for n, p in model.named_parameters():
+        if p.grad is None or id(p) in seen:
+            continue
+        seen.add(id(p))
+        gn.append(n); gv.append(float(p.grad.double().norm()))
+    out["grad_names"] = np.array(gn); out["grad_norms"] = np.array(gv, dtype=np.float64)
+    q = dict(model.named_parameters())["bert.encoder.layer.0.attention_self.query.weight_orig"]
+    out["grad::bert.encoder.layer.0.attention_self.query.weight_orig[:8]"] = q.grad[:8].numpy().copy()
+    mk = masks["bert.encoder.layer.0.attention_self.query.weight_mask"]
+    assert float(q.grad[mk == 0].abs().max()) == 0.0
+    out["state_keys"] = np.array(sorted(model.state_dict().keys()))
+    meta = dict(case=name, family="uc2", layers=layers, vocab=vocab, B=B, R=R, ragged=True, weight_seed=wseed, batch_seed=bseed,
+                mask_density=density, torch=torch.__version__,
+                input_checksum=float(batch["features"].double().sum() + batch["spatials"].double().sum()
+                                     + batch["question"].double().sum()),
+                reference="unmodified reference + torch.nn.utils.prune.CustomFromMask on the train_task_sft.py module list")
+    out["meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print("%s: loss %.6f  (%.1fs)" % (name, loss, time.time() - t0), flush=True)
+
+
 def main(argv):
     ref = ref_shim.import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = argv[1:] or list(CASES)
+    which = argv[1:] or (list(CASES) + ["uc2_L2_B4_sft"])
     for name in which:
-        make_case(ref, name, CASES[name])
+        if name == "uc2_L2_B4_sft":
+            make_sft_case(ref)
+        else:
+            make_case(ref, name, CASES[name])
 
 
 if __name__ == "__main__":

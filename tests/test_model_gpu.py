@@ -198,3 +198,46 @@ def test_dropout_training_mode_statistics():
     loss, _ = TU.ForwardModelsTrain(cfg, task_cfg, DEV, "TASK15", S.batch_tuple(b), model)
     loss.backward()
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_uc2_sft_masks_match_reference_golden(precision):
+    """Sparse fine-tuning (BASELINE configs[3]; train_task_sft.py:L409-461): prune.CustomFromMask installed on the
+    reference's module list; masks live as packed bits inside the engine.  fp32: logits / loss / gradient norms against
+    the unmodified reference; both modes: d/dW_orig exactly 0 where masked, state_dict keys identical."""
+    from clg_vqa_b200 import sft
+    g, meta = _load_golden("uc2_L2_B4_sft")
+    cfg = C.uc2_base(meta["layers"], vocab_size=meta["vocab"])
+    task_cfg = C.gqa_task_cfg(max_region_num=meta["R"])
+    model = BertForVLTasks(cfg, task_cfg, ["TASK15"])
+    model.load_state_dict(S.synth_state_dict(model, seed=meta["weight_seed"]), strict=True)
+    names = sft.uc2_masked_module_names(meta["layers"])
+    masks = sft.synth_mask_dict(model, names, density=meta["mask_density"], seed=meta["weight_seed"])
+    model.load_state_dict(sft.premask_state_dict(model.state_dict(), masks))
+    sft.pruning_model_custom(model, masks, names=names)
+    assert sorted(model.state_dict().keys()) == [str(k) for k in g["state_keys"]]
+    model.set_precision(precision)
+    model.to(DEV)
+    model.eval()
+    b = _batch(meta)
+    loss, score = TU.ForwardModelsTrain(cfg, task_cfg, DEV, "TASK15", S.batch_tuple(b), model)
+    loss.backward()
+    params = dict(model.named_parameters())
+    qn = "bert.encoder.layer.0.attention_self.query.weight_orig"
+    mk = masks["bert.encoder.layer.0.attention_self.query.weight_mask"].to(DEV)
+    gq = params[qn].grad
+    assert torch.equal(gq[mk == 0], torch.zeros_like(gq[mk == 0]))          # bit-exact mask application
+    for n in names:
+        p = params[n + ".weight_orig"]
+        m = masks[n + ".weight_mask"].to(DEV)
+        assert float(p.grad[m == 0].abs().max()) == 0.0, n
+    tol_l, tol_g = (1e-5, 2e-4) if precision == "fp32" else (1e-3, 5e-2)
+    assert abs(float(loss) - float(g["loss_fp32"])) / float(g["loss_fp32"]) <= tol_l * (1 if precision == "fp32" else 10)
+    norms = dict(zip([str(n) for n in g["grad_names"]], g["grad_norms"]))
+    floor = (1e-3 if precision == "fp32" else 1.0) * float(np.median(g["grad_norms"]))
+    for n, ref in norms.items():
+        mine = float(params[n].grad.double().norm())
+        assert abs(mine - ref) / max(ref, floor) <= tol_g, (n, mine, ref)
+    if precision == "fp32":
+        ref = torch.from_numpy(g["grad::" + qn + "[:8]"])
+        assert _rel(gq[:8], ref) <= 2e-4

@@ -128,3 +128,37 @@ def test_loss_edge_cases():
     y = torch.argmax(target.long(), 1)
     assert y.tolist() == [7, 0, 0]
     assert torch.isfinite(loss)
+
+
+def test_oracle_sft_masked_matches_reference():
+    """SFT fixture (unmodified reference + prune.CustomFromMask, oracle/make_golden.py::make_sft_case): the oracle
+    fed W_orig * M reproduces the reference's logits, and d/dW_orig = (d/dW_eff) * M (train_task_sft.py:L432-461)."""
+    from clg_vqa_b200 import sft
+    from clg_vqa_b200.encoders import BertForVLTasks
+    g, meta = _load("uc2_L2_B4_sft")
+    cfg = C.uc2_base(meta["layers"], vocab_size=meta["vocab"])
+    model = BertForVLTasks(cfg, C.gqa_task_cfg(meta["R"]), ["TASK15"])
+    sd = S.synth_state_dict(model, seed=meta["weight_seed"])
+    names = sft.uc2_masked_module_names(meta["layers"])
+    masks = sft.synth_mask_dict(model, names, density=meta["mask_density"], seed=meta["weight_seed"])
+    sd = sft.premask_state_dict(sd, masks)
+    b = S.synth_batch(meta["B"], num_regions=meta["R"], seed=meta["batch_seed"], ragged_regions=True, vocab_size=meta["vocab"])
+    leaves = {}
+    for k in list(sd):
+        ck = S.canonical_key(k)
+        if ck not in leaves:
+            leaves[ck] = sd[ck].clone().requires_grad_(True)
+        sd[k] = leaves[ck]
+    lg = uc2_oracle.uc2_forward(sd, cfg, *_args(b))
+    assert _rel(lg.detach(), g["logits_fp32"]) <= 5e-6
+    loss, _ = loss_oracle.gqa_prior_loss(lg, b["target"], b["distances"], 10.0)
+    assert abs(float(loss) - float(g["loss_fp32"])) / float(g["loss_fp32"]) <= 1e-5
+    loss.backward()
+    qn = "bert.encoder.layer.0.attention_self.query.weight"
+    gq = leaves[qn].grad * masks["bert.encoder.layer.0.attention_self.query.weight_mask"]
+    ref = torch.from_numpy(g["grad::" + qn + "_orig[:8]"])
+    assert float((gq[:8] - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+    assert torch.equal(ref == 0, (masks["bert.encoder.layer.0.attention_self.query.weight_mask"][:8] == 0) | (ref == 0))
+    keys = set(str(k) for k in g["state_keys"])
+    assert qn + "_orig" in keys and qn + "_mask" in keys and qn not in keys
+    assert "bert.encoder.layer.0.attention_self.v_query.weight_mask" in keys
