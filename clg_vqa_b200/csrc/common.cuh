@@ -97,16 +97,28 @@ __device__ __forceinline__ float dgelu_erf(float x) {
 
 // gelu(u) and gelu'(u) together from ONE exponential: erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7,
 // branch-free), whose e^{-x^2} with x = u/sqrt(2) is also the Gaussian of gelu'(u) = Phi(u) + u phi(u).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void gelu_pair_fast(float u, float& g, float& dg) {
-  const float x = u * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, fabsf(x), 1.0f));
-  const float E = __expf(-x * x);
+  // two MUFU ops (rcp, ex2) and ~14 FMA-pipe ops per element, no slow paths / calls: the epilogue of the FFN1
+  // GEMM has to fit under the tile's tensor-core time
+  const float ax = fabsf(u) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
+  const float E = ex2_approx(u * u * -0.72134752044448170368f);        // e^{-u^2/2}
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float erfv = copysignf(1.0f - poly * t * E, x);
-  const float cdf = fmaf(0.5f, erfv, 0.5f);
+  const float q = 0.5f * poly * t * E;                                 // (1 - erf(|x|)) / 2
+  const float cdf = u >= 0.f ? 1.0f - q : q;                           // Phi(u)
   g = u * cdf;
   dg = fmaf(u * E, 0.39894228040143267794f, cdf);
 }

@@ -1,0 +1,100 @@
+"""The four TMA-fed fast epilogues of the tcgen05 GEMM (gemm_epilogue_fast.cuh) against fp64 torch references and
+against the generic epilogue on the same inputs: plain bias -> bf16, bias + dropout + fp32 residual -> fp32,
+bias + GeLU with saved derivative, multiply by a saved bf16 tensor.  Shapes cover ragged M (partial TMA boxes),
+several tiles per persistent CTA, both B major-nesses (forward and dgrad) and odd tile-pair counts."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from clg_vqa_b200 import ops  # noqa: E402
+from clg_vqa_b200.ops import DropSite  # noqa: E402
+
+DEV = "cuda"
+
+
+def _rand(*shape, dtype=torch.float32, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+SHAPES = [(608, 768, 256), (1000, 2304, 320), (19456, 768, 128), (384, 3072, 768), (129, 256, 64)]
+
+
+@pytest.mark.parametrize("b_k", [True, False])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_fast_plain_and_resid(M, N, K, b_k):
+    a = _rand(M, K, dtype=torch.bfloat16, seed=1)
+    w = _rand(N, K, dtype=torch.bfloat16, scale=0.05, seed=2) if b_k else _rand(K, N, dtype=torch.bfloat16, scale=0.05, seed=2)
+    bias = _rand(N, seed=3)
+    res = _rand(M, N, seed=4)
+    lin = a.double() @ (w.double().t() if b_k else w.double())
+    # plain: bias -> bf16 (and without bias)
+    c = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, c, b_kmajor=b_k, bias=bias)
+    assert torch.equal(c, (lin + bias.double()).float().bfloat16()) or _rel(c, lin + bias.double()) < 8e-3
+    c2 = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, c2, b_kmajor=b_k)
+    assert _rel(c2, lin) < 8e-3 and bool(torch.isfinite(c2.float()).all())
+    # residual: fp32
+    y = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(a, w, y, b_kmajor=b_k, bias=bias, residual=res)
+    assert _rel(y, lin + bias.double() + res.double()) < 2e-5
+    y2 = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(a, w, y2, b_kmajor=b_k, residual=res)
+    assert _rel(y2, lin + res.double()) < 2e-5
+    # residual + dropout: identical mask and values as the SIMT backend's generic epilogue
+    site = DropSite(0.1, seed=77, offset=3 << 20)
+    y3 = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(a, w, y3, b_kmajor=b_k, bias=bias, residual=res, dropout=site)
+    y4 = torch.empty(M, N, device=DEV)
+    ops.gemm(a, w, y4, b_kmajor=b_k, bias=bias, residual=res, dropout=site, backend=ops.GEMM_SIMT)
+    assert _rel(y3, y4) < 2e-5
+    dropped = (y3 == res)
+    assert abs(float(dropped.float().mean()) - 0.1) < 0.02
+
+
+@pytest.mark.parametrize("M,N,K", [(608, 3072, 768), (19456, 3072, 64), (300, 256, 128)])
+def test_fast_gelu_pair_and_mul_aux(M, N, K):
+    a = _rand(M, K, dtype=torch.bfloat16, seed=5)
+    w = _rand(N, K, dtype=torch.bfloat16, scale=0.05, seed=6)
+    bias = _rand(N, seed=7)
+    u = a.double() @ w.double().t() + bias.double()
+    h = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    g = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, h, bias=bias, act=ops.ACT_GELU_GRAD, aux_out=g)
+    ref_h = torch.nn.functional.gelu(u)
+    ref_g = 0.5 * (1 + torch.erf(u / math.sqrt(2))) + u * torch.exp(-0.5 * u * u) / math.sqrt(2 * math.pi)
+    assert float((h.double() - ref_h).abs().max()) < 8e-3 * float(ref_h.abs().max())
+    assert float((g.double() - ref_g).abs().max()) < 8e-3
+    # dgrad form: C = (A W) * aux, W consumed as stored ([K_w, N_w] -> MN-major B)
+    a2 = _rand(M, K, dtype=torch.bfloat16, seed=8)
+    w2 = _rand(K, N, dtype=torch.bfloat16, scale=0.05, seed=9)
+    d = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a2, w2, d, b_kmajor=False, act=ops.ACT_MUL_AUX, aux_in=g)
+    ref_d = (a2.double() @ w2.double()) * g.double()
+    assert float((d.double() - ref_d).abs().max()) < 8e-3 * float(ref_d.abs().max())
+
+
+def test_fast_matches_generic_bitwise_fp32():
+    """same accumulation order in both epilogues: the fp32 residual form must agree bit for bit"""
+    import os
+    M, N, K = 1000, 768, 768
+    a = _rand(M, K, dtype=torch.bfloat16, seed=11)
+    w = _rand(N, K, dtype=torch.bfloat16, scale=0.05, seed=12)
+    bias = _rand(N, seed=13)
+    res = _rand(M, N, seed=14)
+    y = torch.empty(M, N, device=DEV)
+    ops.gemm(a, w, y, bias=bias, residual=res)
+    # alpha != 1 is routed to the generic epilogue; alpha = 1 + 0 here via accumulate path is different, so use a
+    # strided (unaligned-for-TMA) output instead: ldc not a multiple of 4 floats
+    big = torch.empty(M, N + 1, device=DEV)
+    yg = big[:, :N]
+    ops.gemm(a, w, yg, bias=bias, residual=res)
+    assert torch.equal(y, yg)
