@@ -525,10 +525,16 @@ int gemm_tc(const clgGemmParams& p, cudaStream_t stream) {
     const int waves = (tiles + sms - 1) / sms;
     return (double)tiles / ((double)waves * sms);
   };
+  // BN = 256 whenever a CTA pair still gets at least one 256 x 256 unit: the cta_group::2 MMA at N = 256 has the
+  // lowest shared-memory traffic per FLOP (measured: the tensor pipe is shared-memory-bandwidth bound at N = 128);
+  // otherwise the tile width with fewer idle SMs in the last wave.
   int bn = 256;
   if (p.N <= 64) bn = 64;
   else if (p.N <= 128) bn = 128;
-  else if (eff(128) > eff(256) + 0.08) bn = 128;
+  else {
+    const int units256 = ((num_m + 1) / 2) * ((p.N + 255) / 256);
+    if (!(p.N % 256 == 0 && units256 >= sms / 2) && eff(128) > eff(256) + 0.08) bn = 128;
+  }
   static const int force_bn = [] { const char* s = getenv("CLG_GEMM_FORCE_BN"); return s ? atoi(s) : 0; }();
   if (force_bn == 256 && p.N > 128) bn = 256;
   if (force_bn == 128 && p.N > 64) bn = 128;
