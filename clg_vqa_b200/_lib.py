@@ -167,6 +167,7 @@ SYMBOLS = {
     "clg_adamw_step": (C.c_int, [C.POINTER(AdamWParams), c_vp]),
     "clg_cast_shadow": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "clg_cast_f32_to_bf16": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "clg_cast_f32_to_bf16_2d": (C.c_int, [c_vp, c_i64, c_vp, c_i64, C.c_int32, C.c_int32, c_vp]),
     "clg_pack_mask": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "clg_apply_mask": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "clg_colsum": (C.c_int, [c_vp, c_i32, c_i64, c_i32, c_i32, c_vp, c_vp]),

@@ -262,7 +262,9 @@ template <typename K> static int set_smem(K kernel, size_t bytes, const char* wh
 
 int attention_tc_fwd(const clgAttentionFwdParams& p, cudaStream_t stream);
 int attention_tc_bwd(const clgAttentionBwdParams& p, cudaStream_t stream);
-static int g_attn_backend = 0;   // 0 auto (tcgen05 when bf16), 1 force FFMA
+int attention_pipe_fwd(const clgAttentionFwdParams& p, cudaStream_t stream);   // persistent pipelined kernels (attention_pipe.cu)
+int attention_pipe_bwd(const clgAttentionBwdParams& p, cudaStream_t stream);
+static int g_attn_backend = 0;   // 0 auto (pipelined tcgen05, then one-CTA-per-head tcgen05, then FFMA), 1 force FFMA, 2 skip the pipelined kernels
 
 }  // namespace clg
 
@@ -274,7 +276,11 @@ extern "C" int clg_attention_fwd(const clgAttentionFwdParams* p, clgStream_t str
   int st = require_sm100();
   if (st != CLG_OK) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (p->dtype == CLG_BF16 && g_attn_backend == 0) {
+  if (p->dtype == CLG_BF16 && g_attn_backend != 1) {
+    if (g_attn_backend != 2) {
+      st = attention_pipe_fwd(*p, s);
+      if (st != CLG_ERR_UNSUPPORTED) return st;
+    }
     st = attention_tc_fwd(*p, s);
     if (st != CLG_ERR_UNSUPPORTED) return st;
   }
@@ -301,7 +307,11 @@ extern "C" int clg_attention_bwd(const clgAttentionBwdParams* p, clgStream_t str
   int st = require_sm100();
   if (st != CLG_OK) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (p->dtype == CLG_BF16 && g_attn_backend == 0) {
+  if (p->dtype == CLG_BF16 && g_attn_backend != 1) {
+    if (g_attn_backend != 2) {
+      st = attention_pipe_bwd(*p, s);
+      if (st != CLG_ERR_UNSUPPORTED) return st;
+    }
     st = attention_tc_bwd(*p, s);
     if (st != CLG_ERR_UNSUPPORTED) return st;
   }

@@ -1,0 +1,686 @@
+// Persistent, warp-specialised tcgen05 attention for the short joint sequence (bf16 mode, d_head = 64,
+// forward S <= 128, backward S <= 96).  Same math and rounding points as attention_tc.cu (which stays the path
+// for longer sequences); what changes is the schedule: the one-CTA-per-(sample, head) kernels were a serial
+// latency chain (TMEM alloc -> TMA -> MMA -> softmax -> MMA -> store) with two resident CTAs per SM.  Here one
+// CTA per SM walks its (sample, head) items with
+//   warp 0      TMA producer: Q/K/V (+ dO, O in the backward) boxes of item i+1.. into a ring of stages
+//   warp 1      MMA issuer:   S = Q K^T (and dP = dO V^T) of item i+1 is issued before the P V (dV/dK/dQ) MMAs
+//                             of item i, so the tensor core never waits for the softmax of the same item
+//   warps 2-5 / 6-9   two softmax groups (128 threads = the 128 TMEM lanes each) working on alternate items,
+//                             each with its own TMEM accumulators, P / dS tiles and output staging
+// Results leave through TMA stores whose box is exactly S rows tall, so nothing of the neighbouring sample is
+// touched.  Scores never reach HBM.
+#include <mutex>
+#include <stdlib.h>
+#include <string.h>
+#include "tc_common.cuh"
+
+namespace clg {
+
+static constexpr int PD = 64;             // head dim
+static constexpr int P_THREADS = 320;
+
+struct AttnPipeArgs {
+  int B, S, H, NP;                        // NP = keys / queries padded to 16
+  int items;                              // B * H
+  int nst;                                // smem stages
+  float scale;
+  const float* key_bias;                  // [B, S]
+  float* lse;                             // [B, H, S]
+  Drop drop;
+};
+
+__device__ __forceinline__ uint32_t psw_off(int row, int col /*0..63*/) {       // SWIZZLE_128B, 128 B rows
+  return (uint32_t)(row * 128 + ((((col >> 3) ^ (row & 7)) << 4)) + ((col & 7) << 1));
+}
+__device__ __forceinline__ void named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ uint32_t pk2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// dropout of 8 consecutive elements whose first index is even: one hash per pair (same bits as drop_keep)
+__device__ __forceinline__ void drop8_even(const Drop& d, uint64_t base, float* p) {
+  const uint32_t i0 = (uint32_t)base >> 1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t h = lowbias32((i0 + k) ^ d.key);
+    p[2 * k] = ((h & 0xffffu) >= d.thresh) ? p[2 * k] * d.scale : 0.f;
+    p[2 * k + 1] = ((h >> 16) >= d.thresh) ? p[2 * k + 1] * d.scale : 0.f;
+  }
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+static constexpr float LOG2E = 1.4426950408889634f;
+static constexpr float LN2 = 0.6931471805599453f;
+
+// barrier slots (8 B each) inside the first KiB of shared memory
+enum { PB_FULL = 0, PB_EMPTY = 4, PB_SRDY = 8, PB_PRDY = 11, PB_ORDY = 14, PB_TFREE = 17, PB_SFREE = 20, PB_COUNT = 23 };
+
+// lane 0's probe result for the whole (converged) warp
+__device__ __forceinline__ bool warp_probe(uint32_t bar, uint32_t parity) {
+  return __shfl_sync(0xffffffffu, mbar_test(bar, parity) ? 1 : 0, 0) != 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// shared memory: [3 KiB: barriers, tmem slot, key bias per group] [nst x (Q | K | V)] [P per group]
+//                [O staging per group] [16 KiB read slack: the M = 128 MMAs read rows NP..127 of the P tiles]
+// TMEM: group g owns TG columns: S in [0, NP), O in [TO, TO + 64) - separate, so S of the group's next item is
+// computed while the current item's P V product and output are still in flight (NG = 3: TG = 160, TO = 96)
+// ------------------------------------------------------------------------------------------------
+template <int NCH, int NG>      // NP = 16 * NCH keys; NG softmax groups (3 when 3 x (S + O) columns fit in TMEM)
+__global__ void __launch_bounds__(64 + 128 * NG, 1)
+attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_ctx, const AttnPipeArgs a) {
+  constexpr int NP = NCH * 16;
+  constexpr int KB = (NP + 63) / 64;
+  constexpr uint32_t TN = (uint32_t)NP * 128u;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  constexpr int TG = NG == 3 ? 160 : 256, TO = NG == 3 ? 96 : 128;
+  static_assert(NG == 2 || NP <= 96, "three groups need S + O <= 160 columns");
+  const int NST = a.nst;
+  const uint32_t sStage = base + 3072;
+  const uint32_t sP0 = sStage + (uint32_t)NST * 3u * TN;
+  const uint32_t sO0 = sP0 + (uint32_t)NG * KB * TN;
+  auto bar = [&](int i) { return base + 8u * (uint32_t)i; };
+  volatile uint32_t* tslot = reinterpret_cast<volatile uint32_t*>(gen + 512);
+  float* kbuf = reinterpret_cast<float*>(gen + 1024);          // key bias (x log2 e) of the current item: [NG][128] fp32
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = a.S, H = a.H;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_ctx);
+    for (int s = 0; s < 4; ++s) { mbar_init(bar(PB_FULL + s), 1); mbar_init(bar(PB_EMPTY + s), 1); }
+    for (int g = 0; g < NG; ++g) {
+      mbar_init(bar(PB_SRDY + g), 1); mbar_init(bar(PB_PRDY + g), 4); mbar_init(bar(PB_ORDY + g), 1); mbar_init(bar(PB_TFREE + g), 4);
+      mbar_init(bar(PB_SFREE + g), 4);
+    }
+    fence_barrier_init(); fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(base + 512, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tslot;
+
+  const int n_it = ((int)blockIdx.x < a.items) ? (a.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    for (int it = 0; it < n_it; ++it) {
+      const int w = (int)blockIdx.x + it * (int)gridDim.x;
+      const int s = it % NST;
+      mbar_wait(bar(PB_EMPTY + s), ((it / NST) & 1) ^ 1u);
+      if (elect_one()) {
+        const int b = w / H, h = w % H;
+        const uint32_t st = sStage + (uint32_t)s * 3u * TN;
+        mbar_expect_tx(bar(PB_FULL + s), 3u * TN);
+        tma_load_2d(st, &tm_qkv, bar(PB_FULL + s), h * PD, b * S);
+        tma_load_2d(st + TN, &tm_qkv, bar(PB_FULL + s), H * PD + h * PD, b * S);
+        tma_load_2d(st + 2 * TN, &tm_qkv, bar(PB_FULL + s), 2 * H * PD + h * PD, b * S);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: issues whichever of {S(next), PV(next)} has its operands ready, so the two
+    // softmax groups never wait on each other ----------------
+    auto issue_s = [&](int it) {
+      const int s = it % NST, g = it % NG;
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t st = sStage + (uint32_t)s * 3u * TN;
+        constexpr uint32_t idesc = make_idesc_mn(128, NP, false, false);
+        const uint32_t tS = tmem + (uint32_t)(g * TG);
+#pragma unroll
+        for (int k = 0; k < PD / 16; ++k)
+          umma_bf16(tS, umma_desc(st + k * 32, 16, 1024), umma_desc(st + TN + k * 32, 16, 1024), idesc, k > 0);
+        umma_commit(bar(PB_SRDY + g));
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int it) {
+      const int s = it % NST, g = it % NG;
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t sV = sStage + (uint32_t)s * 3u * TN + 2 * TN;
+        const uint32_t sP = sP0 + (uint32_t)g * KB * TN;
+        constexpr uint32_t idesc = make_idesc_mn(128, PD, false, true);
+        const uint32_t tO = tmem + (uint32_t)(g * TG + TO);
+#pragma unroll
+        for (int k = 0; k < NP / 16; ++k)
+          umma_bf16(tO, umma_desc(sP + (k >> 2) * TN + (k & 3) * 32, 16, 1024), umma_desc(sV + k * 2048, 8192, 1024), idesc, k > 0);
+        umma_commit(bar(PB_ORDY + g));
+        umma_commit(bar(PB_EMPTY + s));          // Q, K, V of this stage are consumed
+      }
+      __syncwarp();
+    };
+    int ns = 0, npv = 0;
+    while (npv < n_it) {
+      if (npv < ns) {
+        const int g = npv % NG, u = npv / NG;
+        if (warp_probe(bar(PB_PRDY + g), u & 1) && warp_probe(bar(PB_TFREE + g), (u & 1) ^ 1u)) { issue_pv(npv); ++npv; continue; }
+      }
+      if (ns < n_it) {
+        const int s = ns % NST, g = ns % NG, u = ns / NG;
+        if (warp_probe(bar(PB_FULL + s), (ns / NST) & 1) && warp_probe(bar(PB_SFREE + g), (u & 1) ^ 1u)) { issue_s(ns); ++ns; continue; }
+      }
+    }
+  } else {
+    // ---------------- softmax groups ----------------
+    const int g = (warp - 2) >> 2;
+    const int wq = warp & 3;                       // TMEM lane quarter of this warp
+    const int row = wq * 32 + lane;                // query row == TMEM lane
+    const int tg = (warp - 2 - 4 * g) * 32 + lane; // thread index inside the group
+    const bool valid = row < S;
+    const bool in_tile = row < NP;
+    const bool warp_live = wq * 32 < S;
+    float* kb = kbuf + g * 128;                    // key bias * log2(e)
+    const uint32_t sP = sP0 + (uint32_t)g * KB * TN;
+    uint8_t* gP = gen + (sP - base);
+    const uint32_t sO = sO0 + (uint32_t)g * TN;
+    uint8_t* gO = gen + (sO - base);
+    const uint32_t trow = tmem + (uint32_t)(g * TG) + ((uint32_t)(wq * 32) << 16);
+    const float scale2 = a.scale * LOG2E;          // softmax in base 2: p = 2^(s * scale * log2e + kb * log2e - m)
+    const bool even_rows = (S & 1) == 0;           // every row's first dropout index is even: pairwise hashing
+    auto load_kb = [&](int it) -> float {
+      if (it >= n_it || tg >= S) return -INFINITY;
+      const int w = (int)blockIdx.x + it * (int)gridDim.x;
+      return __ldg(a.key_bias + (int64_t)(w / H) * S + tg) * LOG2E;
+    };
+    float kb_next = load_kb(g);
+    for (int it = g; it < n_it; it += NG) {
+      const int u = it / NG;
+      const int w = (int)blockIdx.x + it * (int)gridDim.x;
+      const int b = w / H, h = w % H;
+      const float kbv = kb_next;
+      kb_next = load_kb(it + NG);                  // in flight during this item
+      if (tg == 0) bulk_wait_read<0>();            // the previous TMA store has read the O staging tile
+      named_bar(1 + g, 128);                       // every thread of the group is done with the previous item's key bias
+      if (tg < NP) kb[tg] = kbv;
+      named_bar(1 + g, 128);
+      mbar_wait(bar(PB_SRDY + g), u & 1);
+      __syncwarp();
+      tcgen05_fence_after();
+      float m = -INFINITY, sum = 0.f;
+      if (warp_live) {
+        const uint64_t drow = (((uint64_t)b * H + h) * S + (valid ? row : 0)) * (uint64_t)S;
+        float ex[NP];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tmem_ld16_nowait(trow + c * 16, &ex[c * 16]);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tmem_wait_ld_dep16(&ex[c * 16]);
+        // the scores are in registers: the S columns may be overwritten by the group's next item
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(PB_SFREE + g));
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};       // four independent chains
+#pragma unroll
+        for (int j = 0; j < NP; ++j) { ex[j] = fmaf(ex[j], scale2, kb[j]); m4[j & 3] = fmaxf(m4[j & 3], ex[j]); }
+        m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < NP; ++j) { ex[j] = ex2f(ex[j] - m); s4[j & 3] += ex[j]; }
+        sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        const float inv = valid ? 1.0f / sum : 0.f;
+        if (in_tile) {
+#pragma unroll
+          for (int j8 = 0; j8 < NP; j8 += 8) {
+            float p[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) p[e] = ex[j8 + e] * inv;
+            if (a.drop.on) {
+              if (even_rows) {
+                drop8_even(a.drop, drow + j8, p);                         // columns >= S hold exact zeros already
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) p[e] = drop_apply(a.drop, drow + j8 + e, p[e]);
+              }
+            }
+            *reinterpret_cast<uint4*>(gP + (j8 >> 6) * TN + psw_off(row, j8 & 63)) =
+                make_uint4(pk2(p[0], p[1]), pk2(p[2], p[3]), pk2(p[4], p[5]), pk2(p[6], p[7]));
+          }
+        }
+      } else {
+        if (lane == 0) mbar_arrive(bar(PB_SFREE + g));
+        if (in_tile)
+          for (int j = 0; j < NP; j += 8)
+            *reinterpret_cast<uint4*>(gP + (j >> 6) * TN + psw_off(row, j & 63)) = make_uint4(0, 0, 0, 0);
+      }
+      fence_proxy_async();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(PB_PRDY + g));
+      if (warp_live && valid && a.lse) a.lse[((int64_t)b * H + h) * S + row] = (m + __log2f(sum)) * LN2;
+      mbar_wait(bar(PB_ORDY + g), u & 1);
+      __syncwarp();
+      tcgen05_fence_after();
+      if (warp_live) {
+        float o[64];
+        tmem_ld32_nowait(trow + TO, o);
+        tmem_ld32_nowait(trow + TO + 32, o + 32);
+        tmem_wait_ld_dep32(o);
+        tmem_wait_ld_dep32(o + 32);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(gO + psw_off(row, 8 * j)) =
+                make_uint4(pk2(o[8 * j + 0], o[8 * j + 1]), pk2(o[8 * j + 2], o[8 * j + 3]), pk2(o[8 * j + 4], o[8 * j + 5]),
+                           pk2(o[8 * j + 6], o[8 * j + 7]));
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(PB_TFREE + g));
+      fence_proxy_async();
+      named_bar(1 + g, 128);
+      if (tg == 0) { tma_store_2d(&tm_ctx, sO, h * PD, b * S); bulk_commit(); }
+    }
+    if (tg == 0) bulk_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward (S <= 96)
+// shared memory: [2 KiB header] [nst x (Q | K | V | dO | O)] [g=0: P (2 blocks) | dS (2 blocks)] [g=1: ...] [16 KiB slack]
+// TMEM: group g owns columns [256 g, 256 g + 256): S [0,128) | dP [128,256), then dV [0,64) | dK [64,128) | dQ [128,192)
+// the dQ / dK / dV tiles are staged (bf16, swizzled) in the group's P / dS blocks once the MMAs have consumed them
+// ------------------------------------------------------------------------------------------------
+struct AttnPipeBwdArgs {
+  AttnPipeArgs c;
+  int Hd;                                  // H * 64
+};
+
+template <int NCH>
+__global__ void __launch_bounds__(P_THREADS, 1)
+attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                     const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_dqkv, const AttnPipeBwdArgs ab) {
+  constexpr int NP = NCH * 16;
+  constexpr uint32_t TN = (uint32_t)NP * 128u;
+  const AttnPipeArgs& a = ab.c;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const int NST = a.nst;
+  const uint32_t sStage = base + 3072;
+  const uint32_t sG0 = sStage + (uint32_t)NST * 5u * TN;       // per group: P (2 TN) | dS (2 TN)
+  auto bar = [&](int i) { return base + 8u * (uint32_t)i; };
+  volatile uint32_t* tslot = reinterpret_cast<volatile uint32_t*>(gen + 512);
+  float* kbuf = reinterpret_cast<float*>(gen + 1024);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = a.S, H = a.H;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_o); tma_prefetch_desc(&tm_dqkv);
+    for (int s = 0; s < 4; ++s) { mbar_init(bar(PB_FULL + s), 1); mbar_init(bar(PB_EMPTY + s), 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(bar(PB_SRDY + g), 1); mbar_init(bar(PB_PRDY + g), 4); mbar_init(bar(PB_ORDY + g), 1); mbar_init(bar(PB_TFREE + g), 4);
+    }
+    fence_barrier_init(); fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(base + 512, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tslot;
+  const int n_it = ((int)blockIdx.x < a.items) ? (a.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    for (int it = 0; it < n_it; ++it) {
+      const int w = (int)blockIdx.x + it * (int)gridDim.x;
+      const int s = it % NST;
+      mbar_wait(bar(PB_EMPTY + s), ((it / NST) & 1) ^ 1u);
+      if (elect_one()) {
+        const int b = w / H, h = w % H;
+        const uint32_t st = sStage + (uint32_t)s * 5u * TN;
+        mbar_expect_tx(bar(PB_FULL + s), 5u * TN);
+        tma_load_2d(st, &tm_qkv, bar(PB_FULL + s), h * PD, b * S);
+        tma_load_2d(st + TN, &tm_qkv, bar(PB_FULL + s), H * PD + h * PD, b * S);
+        tma_load_2d(st + 2 * TN, &tm_qkv, bar(PB_FULL + s), 2 * H * PD + h * PD, b * S);
+        tma_load_2d(st + 3 * TN, &tm_do, bar(PB_FULL + s), h * PD, b * S);
+        tma_load_2d(st + 4 * TN, &tm_o, bar(PB_FULL + s), h * PD, b * S);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    auto issue_sdp = [&](int it) {
+      const int s = it % NST, g = it & 1;
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t sQ = sStage + (uint32_t)s * 5u * TN, sK = sQ + TN, sV = sK + TN, sdO = sV + TN;
+        constexpr uint32_t idesc = make_idesc_mn(128, NP, false, false);
+        const uint32_t tS = tmem + (uint32_t)(g * 256), tdP = tS + 128;
+#pragma unroll
+        for (int k = 0; k < PD / 16; ++k) {
+          umma_bf16(tS, umma_desc(sQ + k * 32, 16, 1024), umma_desc(sK + k * 32, 16, 1024), idesc, k > 0);
+          umma_bf16(tdP, umma_desc(sdO + k * 32, 16, 1024), umma_desc(sV + k * 32, 16, 1024), idesc, k > 0);
+        }
+        umma_commit(bar(PB_SRDY + g));
+      }
+      __syncwarp();
+    };
+    auto issue_grad = [&](int it) {
+      const int s = it % NST, g = it & 1;
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t sQ = sStage + (uint32_t)s * 5u * TN, sK = sQ + TN, sdO = sQ + 3 * TN;
+        const uint32_t sP = sG0 + (uint32_t)g * 4u * TN, sdS = sP + 2 * TN;
+        const uint32_t tdV = tmem + (uint32_t)(g * 256), tdK = tdV + 64, tdQ = tdV + 128;
+        // dV[j,d] = sum_i P[i,j] dO[i,d]   A = P^T (MN-major over the [i][j] tile), B = dO (MN-major), K = i
+        // dK[j,d] = sum_i dS[i,j] Q[i,d]   A = dS^T (MN-major),                     B = Q  (MN-major)
+        constexpr uint32_t id_t = make_idesc_mn(128, PD, true, true);
+#pragma unroll
+        for (int k = 0; k < NP / 16; ++k) {
+          umma_bf16(tdV, umma_desc(sP + k * 2048, TN, 1024), umma_desc(sdO + k * 2048, 8192, 1024), id_t, k > 0);
+          umma_bf16(tdK, umma_desc(sdS + k * 2048, TN, 1024), umma_desc(sQ + k * 2048, 8192, 1024), id_t, k > 0);
+        }
+        // dQ[i,d] = sum_j dS[i,j] K[j,d]   A = dS (K-major), B = K (MN-major), K = j
+        constexpr uint32_t id_q = make_idesc_mn(128, PD, false, true);
+#pragma unroll
+        for (int k = 0; k < NP / 16; ++k)
+          umma_bf16(tdQ, umma_desc(sdS + (k >> 2) * TN + (k & 3) * 32, 16, 1024), umma_desc(sK + k * 2048, 8192, 1024), id_q, k > 0);
+        umma_commit(bar(PB_ORDY + g));
+        umma_commit(bar(PB_EMPTY + s));
+      }
+      __syncwarp();
+    };
+    // issue whichever of {S/dP(next), grad(next)} is ready: the two groups' chains stay independent
+    int ns = 0, ngr = 0;
+    while (ngr < n_it) {
+      if (ngr < ns) {
+        const int g = ngr & 1, u = ngr >> 1;
+        if (warp_probe(bar(PB_PRDY + g), u & 1)) { issue_grad(ngr); ++ngr; continue; }
+      }
+      if (ns < n_it) {
+        const int s = ns % NST, g = ns & 1, u = ns >> 1;
+        if (warp_probe(bar(PB_FULL + s), (ns / NST) & 1) && warp_probe(bar(PB_TFREE + g), (u & 1) ^ 1u)) { issue_sdp(ns); ++ns; continue; }
+      }
+    }
+  } else {
+    const int g = (warp - 2) >> 2;
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const int tg = (warp - 2 - 4 * g) * 32 + lane;
+    const bool valid = row < S;
+    const bool in_tile = row < NP;
+    const bool warp_live = wq * 32 < NP;
+    float* kb = kbuf + g * 128;
+    const uint32_t sP = sG0 + (uint32_t)g * 4u * TN, sdS = sP + 2 * TN;
+    uint8_t* gP = gen + (sP - base);
+    uint8_t* gdS = gen + (sdS - base);
+    const uint32_t tbase = tmem + (uint32_t)(g * 256) + ((uint32_t)(wq * 32) << 16);
+    const float scale = a.scale;
+    const float scale2 = a.scale * LOG2E;
+    const bool even_rows = (S & 1) == 0;
+    float kb_next = -INFINITY, lse_next = 0.f;
+    auto load_next = [&](int it) {
+      kb_next = -INFINITY; lse_next = 0.f;
+      if (it >= n_it) return;
+      const int w = (int)blockIdx.x + it * (int)gridDim.x;
+      if (tg < S) kb_next = __ldg(a.key_bias + (int64_t)(w / H) * S + tg) * LOG2E;
+      if (valid) lse_next = __ldg(a.lse + ((int64_t)w) * S + row);      // w = b * H + h
+    };
+    load_next(g);
+    for (int it = g; it < n_it; it += 2) {
+      const int u = it >> 1;
+      const int s = it % NST;
+      const int w = (int)blockIdx.x + it * (int)gridDim.x;
+      const int b = w / H, h = w % H;
+      const float kbv = kb_next, lse_i = lse_next;
+      load_next(it + 2);                           // in flight during this item
+      if (tg == 0) bulk_wait_read<0>();            // the previous dQ/dK/dV stores have read the staging tiles
+      named_bar(1 + g, 128);
+      if (tg < 128) kb[tg] = kbv;
+      named_bar(1 + g, 128);
+      mbar_wait(bar(PB_SRDY + g), u & 1);          // S, dP in TMEM; implies the stage's TMA data has landed
+      __syncwarp();
+      tcgen05_fence_after();
+      if (warp_live) {
+        // D_i = dO_i . O_i from the staged tiles
+        float Di = 0.f;
+        if (valid) {
+          const uint8_t* gdO = gen + (sStage - base) + (uint32_t)s * 5u * TN + 3 * TN;
+          const uint8_t* gOo = gdO + TN;
+#pragma unroll
+          for (int c = 0; c < PD; c += 8) {
+            const uint4 x = *reinterpret_cast<const uint4*>(gdO + psw_off(row, c));
+            const uint4 y = *reinterpret_cast<const uint4*>(gOo + psw_off(row, c));
+            const __nv_bfloat162* xv = reinterpret_cast<const __nv_bfloat162*>(&x);
+            const __nv_bfloat162* yv = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 fx = __bfloat1622float2(xv[t]), fy = __bfloat1622float2(yv[t]);
+              Di = fmaf(fx.x, fy.x, Di); Di = fmaf(fx.y, fy.y, Di);
+            }
+          }
+        }
+        const uint64_t drow = (((uint64_t)b * H + h) * S + (valid ? row : 0)) * (uint64_t)S;
+        // base-2 softmax recompute: p = 2^(s * scale * log2e + kb * log2e - lse * log2e); exact zeros for key columns
+        // >= S (kb = -inf) and for query rows >= S (lse2 = +inf), so no per-element predicates are needed
+        const float lse2 = valid ? lse_i * LOG2E : INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < NP; c += 16) {
+          float sv[16], dv[16];
+          tmem_ld16_nowait(tbase + c, sv);
+          tmem_ld16_nowait(tbase + 128 + c, dv);
+          tmem_wait_ld_dep16(sv);
+          tmem_wait_ld_dep16(dv);
+          float pp[16], dd[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pp[j] = ex2f(fmaf(sv[j], scale2, kb[c + j]) - lse2);
+          if (a.drop.on) {
+            if (even_rows) {
+              const uint32_t i0 = (uint32_t)(drow + c) >> 1;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint32_t hsh = lowbias32((i0 + k) ^ a.drop.key);
+                const bool k0 = (hsh & 0xffffu) >= a.drop.thresh, k1 = (hsh >> 16) >= a.drop.thresh;
+                const float d0 = k0 ? dv[2 * k] * a.drop.scale : 0.f, d1 = k1 ? dv[2 * k + 1] * a.drop.scale : 0.f;
+                dd[2 * k] = pp[2 * k] * (d0 - Di); dd[2 * k + 1] = pp[2 * k + 1] * (d1 - Di);
+                pp[2 * k] = k0 ? pp[2 * k] * a.drop.scale : 0.f; pp[2 * k + 1] = k1 ? pp[2 * k + 1] * a.drop.scale : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const bool keep = drop_keep(a.drop, drow + c + j);
+                const float dp = keep ? dv[j] * a.drop.scale : 0.f;
+                dd[j] = pp[j] * (dp - Di);
+                pp[j] = keep ? pp[j] * a.drop.scale : 0.f;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dd[j] = pp[j] * (dv[j] - Di);
+          }
+          if (in_tile) {
+            const int kblk = c >> 6, cc = c & 63;
+            *reinterpret_cast<uint4*>(gP + kblk * TN + psw_off(row, cc)) = make_uint4(pk2(pp[0], pp[1]), pk2(pp[2], pp[3]), pk2(pp[4], pp[5]), pk2(pp[6], pp[7]));
+            *reinterpret_cast<uint4*>(gP + kblk * TN + psw_off(row, cc + 8)) = make_uint4(pk2(pp[8], pp[9]), pk2(pp[10], pp[11]), pk2(pp[12], pp[13]), pk2(pp[14], pp[15]));
+            *reinterpret_cast<uint4*>(gdS + kblk * TN + psw_off(row, cc)) = make_uint4(pk2(dd[0], dd[1]), pk2(dd[2], dd[3]), pk2(dd[4], dd[5]), pk2(dd[6], dd[7]));
+            *reinterpret_cast<uint4*>(gdS + kblk * TN + psw_off(row, cc + 8)) = make_uint4(pk2(dd[8], dd[9]), pk2(dd[10], dd[11]), pk2(dd[12], dd[13]), pk2(dd[14], dd[15]));
+          }
+        }
+        if (in_tile) {
+          for (int c = NP; c < 128; c += 8) {          // unused key columns are read as M rows of the transposed MMAs
+            *reinterpret_cast<uint4*>(gP + (c >> 6) * TN + psw_off(row, c & 63)) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(gdS + (c >> 6) * TN + psw_off(row, c & 63)) = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+      fence_proxy_async();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(PB_PRDY + g));
+      mbar_wait(bar(PB_ORDY + g), u & 1);          // dV, dK, dQ in TMEM; P / dS tiles are free again
+      __syncwarp();
+      tcgen05_fence_after();
+      if (wq * 32 < S) {
+        // staging: dQ -> P block 0, dK -> P block 1, dV -> dS block 0 (S rows x 128 B each)
+        uint8_t* stg[3] = {gP, gP + TN, gdS};
+        const uint32_t src[3] = {tbase + 128, tbase + 64, tbase};
+        const float mul[3] = {scale, scale, 1.f};
+#pragma unroll
+        for (int which = 0; which < 3; ++which) {
+          float o[64];
+          tmem_ld32_nowait(src[which], o);
+          tmem_ld32_nowait(src[which] + 32, o + 32);
+          tmem_wait_ld_dep32(o);
+          tmem_wait_ld_dep32(o + 32);
+          if (valid) {
+            const float sc = mul[which];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(stg[which] + psw_off(row, 8 * j)) =
+                  make_uint4(pk2(o[8 * j + 0] * sc, o[8 * j + 1] * sc), pk2(o[8 * j + 2] * sc, o[8 * j + 3] * sc),
+                             pk2(o[8 * j + 4] * sc, o[8 * j + 5] * sc), pk2(o[8 * j + 6] * sc, o[8 * j + 7] * sc));
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(PB_TFREE + g));
+      fence_proxy_async();
+      named_bar(1 + g, 128);
+      if (tg == 0) {
+        tma_store_2d(&tm_dqkv, sP, h * PD, b * S);
+        tma_store_2d(&tm_dqkv, sP + TN, ab.Hd + h * PD, b * S);
+        tma_store_2d(&tm_dqkv, sdS, 2 * ab.Hd + h * PD, b * S);
+        bulk_commit();
+      }
+    }
+    if (tg == 0) bulk_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+static int make_tmap_rows(CUtensorMap* m, const void* ptr, int64_t cols, int64_t rows, int64_t ld, int box_rows) {
+  return make_tmap_bf16(m, ptr, cols, rows, ld, box_rows);        // box = 64 columns x box_rows, 128B swizzle
+}
+
+static bool pipe_enabled() {
+  static const bool v = [] { const char* s = getenv("CLG_ATTN_PIPE"); return !(s && s[0] == '0'); }();
+  return v;
+}
+
+static int fwd_pipe_smem(int NP, int nst, int ng) {
+  const int KB = (NP + 63) / 64, TN = NP * 128;
+  return 1024 + 3072 + nst * 3 * TN + ng * KB * TN + ng * TN + 16384;
+}
+static int bwd_pipe_smem(int NP, int nst) {
+  const int TN = NP * 128;
+  return 1024 + 3072 + nst * 5 * TN + 8 * TN + 16384;
+}
+static constexpr int P_SMEM_MAX = 232448;
+
+template <int NCH>
+static int launch_pipe_fwd(const CUtensorMap& tq, const CUtensorMap& tc, const AttnPipeArgs& a, int smem, cudaStream_t stream) {
+  constexpr int NG = NCH <= 6 ? 3 : 2;
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] { err = cudaFuncSetAttribute(attn_pipe_fwd_kernel<NCH, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_MAX); });
+  CLG_CUDA_OK(err, "cudaFuncSetAttribute(attn_pipe_fwd)");
+  const int grid = a.items < num_sms() ? a.items : num_sms();
+  attn_pipe_fwd_kernel<NCH, NG><<<grid, 64 + 128 * NG, smem, stream>>>(tq, tc, a);
+  return check_launch("attn_pipe_fwd_kernel");
+}
+
+template <int NCH>
+static int launch_pipe_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& to, const CUtensorMap& tdq,
+                           const AttnPipeBwdArgs& a, int smem, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] { err = cudaFuncSetAttribute(attn_pipe_bwd_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_MAX); });
+  CLG_CUDA_OK(err, "cudaFuncSetAttribute(attn_pipe_bwd)");
+  const int grid = a.c.items < num_sms() ? a.c.items : num_sms();
+  attn_pipe_bwd_kernel<NCH><<<grid, P_THREADS, smem, stream>>>(tq, tdo, to, tdq, a);
+  return check_launch("attn_pipe_bwd_kernel");
+}
+
+// returns CLG_ERR_UNSUPPORTED when the shape is outside the pipelined kernels' range (caller falls back)
+int attention_pipe_fwd(const clgAttentionFwdParams& p, cudaStream_t stream) {
+  if (!pipe_enabled() || p.dtype != CLG_BF16 || p.S > 128 || p.S < 1) return CLG_ERR_UNSUPPORTED;
+  const int NP = (p.S + 15) / 16 * 16;
+  const int ng = NP <= 96 ? 3 : 2;
+  int nst = 3;
+  while (nst > 2 && fwd_pipe_smem(NP, nst, ng) > P_SMEM_MAX) --nst;
+  if (fwd_pipe_smem(NP, nst, ng) > P_SMEM_MAX) return CLG_ERR_UNSUPPORTED;
+  if ((p.ld_ctx * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(p.ctx) & 15)) return CLG_ERR_UNSUPPORTED;
+  CUtensorMap tq, tc;
+  const int64_t rows = (int64_t)p.B * p.S;
+  int st = make_tmap_rows(&tq, p.qkv, 3LL * p.H * PD, rows, p.ld_qkv, NP);
+  if (st != CLG_OK) return st;
+  st = make_tmap_rows(&tc, p.ctx, (int64_t)p.H * PD, rows, p.ld_ctx, p.S);
+  if (st != CLG_OK) return st;
+  AttnPipeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = p.B; a.S = p.S; a.H = p.H; a.NP = NP; a.items = p.B * p.H; a.nst = nst;
+  a.scale = p.scale; a.key_bias = p.key_bias; a.lse = p.lse;
+  a.drop = make_drop(p.dropout);
+  const int smem = fwd_pipe_smem(NP, nst, ng);
+  switch (NP / 16) {
+    case 1: return launch_pipe_fwd<1>(tq, tc, a, smem, stream);
+    case 2: return launch_pipe_fwd<2>(tq, tc, a, smem, stream);
+    case 3: return launch_pipe_fwd<3>(tq, tc, a, smem, stream);
+    case 4: return launch_pipe_fwd<4>(tq, tc, a, smem, stream);
+    case 5: return launch_pipe_fwd<5>(tq, tc, a, smem, stream);
+    case 6: return launch_pipe_fwd<6>(tq, tc, a, smem, stream);
+    case 7: return launch_pipe_fwd<7>(tq, tc, a, smem, stream);
+    case 8: return launch_pipe_fwd<8>(tq, tc, a, smem, stream);
+    default: return CLG_ERR_UNSUPPORTED;
+  }
+}
+
+int attention_pipe_bwd(const clgAttentionBwdParams& p, cudaStream_t stream) {
+  if (!pipe_enabled() || p.dtype != CLG_BF16 || p.S > 96 || p.S < 1) return CLG_ERR_UNSUPPORTED;
+  const int NP = (p.S + 15) / 16 * 16;
+  const int nst = 2;                                                  // >= 2 stages (see the forward)
+  if (bwd_pipe_smem(NP, nst) > P_SMEM_MAX) return CLG_ERR_UNSUPPORTED;
+  if ((p.ld_dqkv * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(p.dqkv) & 15)) return CLG_ERR_UNSUPPORTED;
+  CUtensorMap tq, tdo, to, tdq;
+  const int64_t rows = (int64_t)p.B * p.S;
+  int st = make_tmap_rows(&tq, p.qkv, 3LL * p.H * PD, rows, p.ld_qkv, NP);
+  if (st != CLG_OK) return st;
+  st = make_tmap_rows(&tdo, p.dctx, (int64_t)p.H * PD, rows, p.ld_dctx, NP);
+  if (st != CLG_OK) return st;
+  st = make_tmap_rows(&to, p.ctx, (int64_t)p.H * PD, rows, p.ld_ctx, NP);
+  if (st != CLG_OK) return st;
+  st = make_tmap_rows(&tdq, p.dqkv, 3LL * p.H * PD, rows, p.ld_dqkv, p.S);
+  if (st != CLG_OK) return st;
+  AttnPipeBwdArgs ab;
+  memset(&ab, 0, sizeof(ab));
+  AttnPipeArgs& a = ab.c;
+  a.B = p.B; a.S = p.S; a.H = p.H; a.NP = NP; a.items = p.B * p.H; a.nst = nst;
+  a.scale = p.scale; a.key_bias = p.key_bias; a.lse = const_cast<float*>(p.lse);
+  a.drop = make_drop(p.dropout);
+  ab.Hd = p.H * PD;
+  const int smem = bwd_pipe_smem(NP, nst);
+  switch (NP / 16) {
+    case 1: return launch_pipe_bwd<1>(tq, tdo, to, tdq, ab, smem, stream);
+    case 2: return launch_pipe_bwd<2>(tq, tdo, to, tdq, ab, smem, stream);
+    case 3: return launch_pipe_bwd<3>(tq, tdo, to, tdq, ab, smem, stream);
+    case 4: return launch_pipe_bwd<4>(tq, tdo, to, tdq, ab, smem, stream);
+    case 5: return launch_pipe_bwd<5>(tq, tdo, to, tdq, ab, smem, stream);
+    case 6: return launch_pipe_bwd<6>(tq, tdo, to, tdq, ab, smem, stream);
+    default: return CLG_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace clg

@@ -20,6 +20,16 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __rest
     for (int64_t i = (n8 << 3) + threadIdx.x; i < n; i += blockDim.x) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+__global__ void cast_f32_bf16_2d_kernel(const float* __restrict__ src, int64_t ld_src, bf16* __restrict__ dst, int64_t ld_dst,
+                                        int rows, int cols) {
+  const int64_t total = (int64_t)rows * ld_dst;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld_dst;
+    const int c = (int)(i - r * ld_dst);
+    dst[i] = __float2bfloat16_rn(c < cols ? src[r * ld_src + c] : 0.f);
+  }
+}
+
 __global__ void pack_mask_kernel(const float* __restrict__ mask, uint32_t* __restrict__ bits, int64_t n) {
   // one warp packs 32 consecutive elements into one word with a ballot
   const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -168,6 +178,18 @@ extern "C" int clg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, clgS
   if (n == 0) return CLG_OK;
   cast_f32_bf16_kernel<<<ew_grid(n / 8 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, (bf16*)dst, n);
   return check_launch("cast_f32_bf16_kernel");
+}
+
+extern "C" int clg_cast_f32_to_bf16_2d(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t rows, int32_t cols,
+                                       clgStream_t stream) {
+  using namespace clg;
+  if (!src || !dst || rows < 0 || cols < 0 || ld_src < cols || ld_dst < cols) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  if (rows == 0 || cols == 0) return CLG_OK;
+  cast_f32_bf16_2d_kernel<<<ew_grid((int64_t)rows * ld_dst, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, ld_src, (bf16*)dst, ld_dst, rows, cols);
+  return check_launch("cast_f32_bf16_2d_kernel");
 }
 
 extern "C" int clg_pack_mask(const float* mask, uint32_t* bits, int64_t n, clgStream_t stream) {

@@ -436,8 +436,15 @@ class Engine:
             ws["de_txt"] = E(Mt, d)
             ws["ds"] = E(Mr, d); ws["dg"] = E(Mr, d, dtype=lp); ws["dl"] = E(Mr, d, dtype=lp)
             ws["dpre"] = E(B, P)
+            ws["dpre_lp"] = E(B, P, dtype=lp) if lp != f32 else ws["dpre"]
             for task, hw in heads.items():
                 hw["dhln"] = E(B, hw["C"]); hw["dhc"] = E(B, hw["C"])
+                if lp != f32:
+                    # bf16 GEMM operands of the head backward (tensor-core path); the logit gradient gets a
+                    # 16 B-aligned row pitch (1842 -> 1848) so TMA can fetch it
+                    a_pad = (hw["A"] + 7) // 8 * 8
+                    hw["dl_lp"] = E(B, a_pad, dtype=lp)[:, :hw["A"]]
+                    hw["dhc_lp"] = E(B, hw["C"], dtype=lp)
         self._ws[key] = ws
         return ws
 
@@ -618,7 +625,11 @@ class Engine:
         clf = self.model.clfs_dict[task].logit_fc
         P = self.cfg.pooler_size
         C, A = hw["C"], hw["A"]
+        bf = ws["lp"] == torch.bfloat16
         ops.colsum(dl, self._gvec(self.b_slot[id(clf[3])], A))
+        if bf:      # bf16 operand copies: every GEMM of the head backward runs on the tcgen05 path
+            ops.cast_f32_to_bf16_2d(dl, hw["dl_lp"])
+            dl = hw["dl_lp"]
         self._wgrad(dl, hw["hln"], clf[3], A, C)
         ops.gemm(dl, self._w(clf[3], A, C), hw["dhln"], b_kmajor=False)
         ln = clf[2]
@@ -626,14 +637,22 @@ class Engine:
                           dgamma=self.grad_view(ln.weight), dbeta=self.grad_view(ln.bias))
         ops.act_bwd(hw["dhc"], hw["uc"], hw["dhc"], ops.ACT_DGELU)
         ops.colsum(hw["dhc"], self._gvec(self.b_slot[id(clf[0])], C))
-        self._wgrad(hw["dhc"], ws["pooled"], clf[0], C, P)
-        ops.gemm(hw["dhc"], self._w(clf[0], C, P), ws["dpre"], b_kmajor=False, dropout=site_pool, drop_before_act=True,
+        dhc = hw["dhc"]
+        if bf:
+            ops.cast_f32_to_bf16(hw["dhc"], hw["dhc_lp"])
+            dhc = hw["dhc_lp"]
+        self._wgrad(dhc, ws["pooled"], clf[0], C, P)
+        ops.gemm(dhc, self._w(clf[0], C, P), ws["dpre"], b_kmajor=False, dropout=site_pool, drop_before_act=True,
                  act=pool_dact, aux_in=ws["pact"])
         ops.colsum(ws["dpre"], self._gvec(self.b_slot[id(pmod)], P))
+        dpre = ws["dpre"]
+        if bf:
+            ops.cast_f32_to_bf16(ws["dpre"], ws["dpre_lp"])
+            dpre = ws["dpre_lp"]
         x_first = x_lp.view(B, S * d)[:, :d]
-        self._wgrad(ws["dpre"], x_first, pmod, P, d)
+        self._wgrad(dpre, x_first, pmod, P, d)
         ws["dx"].zero_()
-        ops.gemm(ws["dpre"], self._w(pmod, P, d), ws["dx"].view(B, S * d)[:, :d], b_kmajor=False)
+        ops.gemm(dpre, self._w(pmod, P, d), ws["dx"].view(B, S * d)[:, :d], b_kmajor=False)
 
     def _layer_bwd(self, ws, lw, x_in, x_in_lp, kb, B, S, qmod, omod, ln1, f1mod, f2mod, ln2, scale, site_p, site_o, site_f,
                    row_valid=None):

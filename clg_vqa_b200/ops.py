@@ -301,6 +301,15 @@ def cast_f32_to_bf16(src, dst):
     _count()
 
 
+def cast_f32_to_bf16_2d(src, dst):
+    """dst[:, :cols] = bf16(src); dst's padding columns (row pitch > cols) are zeroed"""
+    _need_cuda(src, dst)
+    rows, cols = src.shape
+    L.check(L.load().clg_cast_f32_to_bf16_2d(src.data_ptr(), _ld(src), dst.data_ptr(), _ld(dst), int(rows), int(cols), _stream()),
+            "clg_cast_f32_to_bf16_2d")
+    _count()
+
+
 def pack_mask(mask, bits, n=None):
     _need_cuda(mask, bits)
     L.check(L.load().clg_pack_mask(mask.data_ptr(), bits.data_ptr(), mask.numel() if n is None else n, _stream()), "clg_pack_mask")

@@ -317,6 +317,10 @@ int clg_cast_shadow(const float* p, int64_t n, const int32_t* chunk_tensor, cons
  * ---------------------------------------------------------------------------------------------- */
 /* dst[i] = bf16(src[i]) (region features, 2048-d fp32 -> bf16 GEMM operand) */
 int clg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, clgStream_t stream);
+/* dst[r*ld_dst + c] = bf16(src[r*ld_src + c]) for c < cols, 0 for cols <= c < ld_dst (row-padded bf16 GEMM operand:
+ * the [B, 1842] logit gradient needs a 16 B-aligned row pitch for TMA) */
+int clg_cast_f32_to_bf16_2d(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t rows, int32_t cols,
+                            clgStream_t stream);
 /* bits[i/32] bit (i%32) = (mask[i] != 0); n multiple of 32 not required (tail bits are 0) */
 int clg_pack_mask(const float* mask, uint32_t* bits, int64_t n, clgStream_t stream);
 /* w[i] *= bit(i)  (pre-zeroing of masked weights, train_task_sft.py:L432-453) */
