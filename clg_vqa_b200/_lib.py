@@ -40,6 +40,7 @@ class GemmParams(C.Structure):
         ("accumulate", c_i32), ("drop_before_act", c_i32),
         ("dropout", Dropout),
         ("backend", c_i32), ("split_k", c_i32),
+        ("colsum", c_vp),
     ]
 
 

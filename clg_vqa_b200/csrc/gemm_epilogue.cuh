@@ -18,6 +18,7 @@ struct EpiArgs {
   int accumulate;     // 0: store, 1: C += v (plain RMW), 2: C += v (atomic; split-K)
   int drop_before_act;
   Drop drop;
+  float* colsum;      // optional [N]: += column sums of the epilogue result
 };
 
 inline EpiArgs make_epi(const clgGemmParams& p) {
@@ -34,7 +35,24 @@ inline EpiArgs make_epi(const clgGemmParams& p) {
   e.accumulate = p.accumulate ? 1 : 0;
   e.drop_before_act = p.drop_before_act;
   e.drop = make_drop(p.dropout);
+  e.colsum = p.colsum;
   return e;
+}
+
+// Column sums of a [32 lanes (rows)] x [32 columns] register tile: a reduce-scatter over the warp (16 + 8 + 4 + 2 + 1
+// shuffles); lane l returns the sum of column l.  Destroys v.
+__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float keep = upper ? v[k + off] : v[k];
+      const float send = upper ? v[k] : v[k + off];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
 }
 
 __device__ __forceinline__ float epi_scalar(const EpiArgs& e, int row, int col, float acc) {
@@ -171,6 +189,10 @@ __device__ __forceinline__ void epi_row_chunk(const EpiArgs& e, int row, int col
         for (int j = 0; j < W; ++j) v[j] *= mask_bit(e.mask_bits, (int64_t)(eidx + j)) ? 1.f : 0.f;
       }
     }
+    if (e.colsum) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) atomicAdd(e.colsum + col0 + j, v[j]);
+    }
     if (e.c_dtype == CLG_BF16) {
       if (e.accumulate) {
         bf16* c = (bf16*)e.C + (int64_t)row * e.ldc + col0;
@@ -218,6 +240,7 @@ __device__ __forceinline__ void epi_row_chunk(const EpiArgs& e, int row, int col
     if (j >= ncols) break;
     const int col = col0 + j;
     const float r = epi_scalar(e, row, col, acc[j]);
+    if (e.colsum) atomicAdd(e.colsum + col, r);
     const int64_t ci = (int64_t)row * e.ldc + col;
     if (e.c_dtype == CLG_BF16) {
       bf16* c = (bf16*)e.C;

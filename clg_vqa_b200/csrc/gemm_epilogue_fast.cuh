@@ -90,6 +90,7 @@ inline int classify_epilogue(const EpiArgs& e) {
     return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ((ld * esz) & 15) == 0;
   };
   if (e.alpha != 1.0f || e.mask_bits || e.accumulate || (e.N % 32) != 0) return EPI_GENERIC;
+  if (e.colsum && e.act != CLG_ACT_MUL_AUX) return EPI_GENERIC;
   if (e.bias && (reinterpret_cast<uintptr_t>(e.bias) & 15)) return EPI_GENERIC;
   const bool c_bf16 = e.c_dtype == CLG_BF16 && al16(e.C, e.ldc, 2);
   const bool c_f32 = e.c_dtype == CLG_F32 && al16(e.C, e.ldc, 4);
@@ -238,6 +239,10 @@ struct FastEpi {
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) { tma_store_2d(tm_c, obox(0), col, row0); bulk_commit(); }
+      if (e.colsum) {           // fused bias gradient of the layer below (rows beyond M are exact zeros: OOB boxes)
+        const float cs = warp_colsum32(acc, lane);
+        atomicAdd(e.colsum + col + lane, cs);
+      }
     }
   }
 };

@@ -271,6 +271,14 @@ __device__ __forceinline__ void tc_epi_chunk(const EpiArgs& e, float* stg, int r
     }
   }
   stage_store_any(stg, e.C, e.c_dtype, e.ldc, r0, c0, e.M, lane, v, e.accumulate);
+  if (e.colsum) {
+    if (row >= e.M) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+    const float cs = warp_colsum32(v, lane);
+    atomicAdd(e.colsum + c0 + lane, cs);
+  }
 }
 
 }  // namespace clg

@@ -665,9 +665,12 @@ class Engine:
                           dbias=self._gvec(self.b_slot[id(f2mod)], d), dropout_in=site_f,
                           row_valid=row_valid, valid_post=row_valid is not None)
         self._wgrad(dgo, lw["h"], f2mod, d, F)
-        ops.gemm(dgo, self._w(f2mod, d, F), ws["du"], b_kmajor=False,
-                 act=ops.ACT_MUL_AUX if ws["lp"] == torch.bfloat16 else ops.ACT_DGELU, aux_in=lw["u"])
-        ops.colsum(ws["du"], self._gvec(self.b_slot[id(f1mod)], F))
+        if ws["lp"] == torch.bfloat16:      # FFN1 bias gradient = column sums of dU, reduced inside the GEMM epilogue
+            ops.gemm(dgo, self._w(f2mod, d, F), ws["du"], b_kmajor=False, act=ops.ACT_MUL_AUX, aux_in=lw["u"],
+                     colsum=self._gvec(self.b_slot[id(f1mod)], F))
+        else:
+            ops.gemm(dgo, self._w(f2mod, d, F), ws["du"], b_kmajor=False, act=ops.ACT_DGELU, aux_in=lw["u"])
+            ops.colsum(ws["du"], self._gvec(self.b_slot[id(f1mod)], F))
         self._wgrad(ws["du"], lw["x1_lp"], f1mod, F, d)
         ops.gemm(ws["du"], self._w(f1mod, F, d), dx, b_kmajor=False, residual=dy)
         # LN1

@@ -81,7 +81,7 @@ def _ld(t: torch.Tensor) -> int:
 
 def gemm(a, b, c, *, a_kmajor=True, b_kmajor=True, M=None, N=None, K=None, alpha=1.0, act=ACT_NONE, bias=None,
          residual=None, aux_in=None, aux_out=None, mask_bits=None, accumulate=False, dropout: DropSite = NO_DROP,
-         drop_before_act=False, backend=GEMM_AUTO, split_k=0):
+         drop_before_act=False, backend=GEMM_AUTO, split_k=0, colsum=None):
     """C[M,N] = epi(alpha * A(m,k) B(n,k)).  a: [M,K] if a_kmajor else [K,M]; b: [N,K] if b_kmajor else [K,N]."""
     _need_cuda(a, b, c)
     if M is None:
@@ -109,6 +109,7 @@ def gemm(a, b, c, *, a_kmajor=True, b_kmajor=True, M=None, N=None, K=None, alpha
     p.drop_before_act = int(bool(drop_before_act))
     p.dropout = dropout.c()
     p.backend, p.split_k = int(backend), int(split_k)
+    p.colsum = _ptr(colsum)
     rec = _gemm_timing
     if rec is not None:
         # same predicate as clg_gemm's auto dispatch: these launches run gemm_tc_kernel

@@ -115,6 +115,8 @@ typedef struct {
   clgDropout dropout;
   int32_t backend;         /* clgGemmBackend */
   int32_t split_k;         /* 0 = auto (TC backend, act==NONE && no bias only) */
+  float* colsum;           /* optional [N]: colsum[n] += sum_m (epilogue result, before rounding to c_dtype); the bias
+                              gradient of the layer that produced A's pre-activation, fused into the dgrad GEMM */
 } clgGemmParams;
 
 int clg_gemm(const clgGemmParams* p, clgStream_t stream);

@@ -98,3 +98,24 @@ def test_fast_matches_generic_bitwise_fp32():
     yg = big[:, :N]
     ops.gemm(a, w, yg, bias=bias, residual=res)
     assert torch.equal(y, yg)
+
+
+@pytest.mark.parametrize("backend", [ops.GEMM_AUTO, ops.GEMM_SIMT])
+def test_fused_colsum_matches_separate(backend):
+    """bias gradient fused into the dgrad epilogue: colsum[n] += sum_m C[m, n] (fast MUL_AUX form and generic forms)"""
+    M, N, K = 1000, 768, 256
+    a = _rand(M, K, dtype=torch.bfloat16, seed=21)
+    w = _rand(K, N, dtype=torch.bfloat16, scale=0.05, seed=22)
+    g = _rand(M, N, dtype=torch.bfloat16, seed=23)
+    d = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    cs = torch.full((N,), 3.0, device=DEV)
+    ops.gemm(a, w, d, b_kmajor=False, act=ops.ACT_MUL_AUX, aux_in=g, colsum=cs, backend=backend)
+    ref = ((a.double() @ w.double()) * g.double())
+    assert _rel(cs, 3.0 + ref.sum(0)) < 1e-4
+    assert float((d.double() - ref).abs().max()) < 8e-3 * float(ref.abs().max())
+    # generic tcgen05 epilogue (fp32 output, bias) with the fused column sums
+    y = torch.empty(M, N, device=DEV)
+    cs2 = torch.zeros(N, device=DEV)
+    bias = _rand(N, seed=24)
+    ops.gemm(a, w, y, b_kmajor=False, bias=bias, colsum=cs2, backend=backend)
+    assert _rel(cs2, (a.double() @ w.double() + bias.double()).sum(0)) < 1e-4
