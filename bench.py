@@ -242,11 +242,17 @@ def run_ours(args):
             step(resident[i % NB])
 
     losses = []
+    pf_state = {}
 
     def loop_e2e(n):
-        for i in range(n):
-            loss, _ = step(host[i % NB])          # H2D of this step's inputs inside ForwardModelsTrain
-            losses.append(float(loss))            # D2H read of the step's loss
+        # every step's inputs come from pinned HOST memory: DevicePrefetcher issues the H2D copy of batch i+1 on a side
+        # stream while step i computes (all n copies happen inside the timed region), and every step's loss is read back
+        from clg_vqa_b200.data import DevicePrefetcher
+        pf = DevicePrefetcher((host[i % NB] for i in range(n)), dev, reuse=pf_state.get("pf"))
+        pf_state["pf"] = pf
+        for batch in pf:
+            loss, _ = step(batch)
+            losses.append(float(loss.detach()))   # D2H read of the step's loss
 
     # warm-up (also builds arenas / workspaces)
     loop_resident(max(3, args.warmup))
@@ -257,6 +263,8 @@ def run_ours(args):
     ms = timed(loop_resident, args.steps)
     launches = ops.launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
+    loop_e2e(2)                                   # untimed: device slots / copy stream of the input pipeline exist
+    losses.clear()
     ms_e2e = timed(loop_e2e, args.steps)
 
     # dominant kernel (tcgen05 GEMM) timed live with CUDA events on the launching stream

@@ -1,6 +1,7 @@
 // Status plumbing, device checks, struct-size probes and the GEMM dispatcher of the C ABI.
 #include <mutex>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -39,6 +40,10 @@ static const DevInfo& dev_info() {
 }
 
 int num_sms() { const int s = dev_info().sms; return s > 0 ? s : 148; }
+bool pdl_enabled() {
+  static const bool v = [] { const char* s = getenv("CLG_PDL"); return !(s && s[0] == '0'); }();
+  return v;
+}
 int require_sm100() { return dev_info().major == 10 ? CLG_OK : CLG_ERR_ARCH; }
 
 int gemm_tc(const clgGemmParams& p, cudaStream_t stream);

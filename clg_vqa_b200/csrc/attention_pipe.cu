@@ -95,6 +95,7 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = a.S, H = a.H;
+  pdl_trigger();
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_ctx);
@@ -110,6 +111,7 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tslot;
+  pdl_wait();
 
   const int n_it = ((int)blockIdx.x < a.items) ? (a.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
@@ -321,6 +323,7 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = a.S, H = a.H;
+  pdl_trigger();
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_o); tma_prefetch_desc(&tm_dqkv);
@@ -335,6 +338,7 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tslot;
+  pdl_wait();
   const int n_it = ((int)blockIdx.x < a.items) ? (a.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0) {
@@ -598,7 +602,7 @@ static int launch_pipe_fwd(const CUtensorMap& tq, const CUtensorMap& tc, const A
   std::call_once(once, [] { err = cudaFuncSetAttribute(attn_pipe_fwd_kernel<NCH, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_MAX); });
   CLG_CUDA_OK(err, "cudaFuncSetAttribute(attn_pipe_fwd)");
   const int grid = a.items < num_sms() ? a.items : num_sms();
-  attn_pipe_fwd_kernel<NCH, NG><<<grid, 64 + 128 * NG, smem, stream>>>(tq, tc, a);
+  CLG_CUDA_OK(launch_pdl(attn_pipe_fwd_kernel<NCH, NG>, dim3(grid), dim3(64 + 128 * NG), (size_t)smem, stream, tq, tc, a), "launch(attn_pipe_fwd)");
   return check_launch("attn_pipe_fwd_kernel");
 }
 
@@ -610,7 +614,7 @@ static int launch_pipe_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const 
   std::call_once(once, [] { err = cudaFuncSetAttribute(attn_pipe_bwd_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_MAX); });
   CLG_CUDA_OK(err, "cudaFuncSetAttribute(attn_pipe_bwd)");
   const int grid = a.c.items < num_sms() ? a.c.items : num_sms();
-  attn_pipe_bwd_kernel<NCH><<<grid, P_THREADS, smem, stream>>>(tq, tdo, to, tdq, a);
+  CLG_CUDA_OK(launch_pdl(attn_pipe_bwd_kernel<NCH>, dim3(grid), dim3(P_THREADS), (size_t)smem, stream, tq, tdo, to, tdq, a), "launch(attn_pipe_bwd)");
   return check_launch("attn_pipe_bwd_kernel");
 }
 

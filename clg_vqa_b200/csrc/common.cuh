@@ -22,6 +22,29 @@ int check_launch(const char* where);   // cudaGetLastError -> status
     if (_e != cudaSuccess) { clg::set_cuda_error(_e, where); return CLG_ERR_CUDA; } \
   } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the next kernel of the stream is launched while this one drains; its prologue
+// (barrier init, TMEM allocation, descriptor prefetch, index math) overlaps our tail.  Device side: pdl_trigger() at
+// the top lets the dependents be scheduled, pdl_wait() blocks until every prerequisite grid has completed and its
+// memory is visible - it precedes the first global access of the kernel.
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+bool pdl_enabled();            // CLG_PDL=0 disables the launch attribute (kernels then run fully serialised)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int num_sms();                 // of the current device (cached)
 int require_sm100();           // CLG_OK or CLG_ERR_ARCH for the current device (cached)
 

@@ -79,6 +79,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
@@ -102,6 +103,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (MC) cluster_sync_all();          // the peer's barriers must be initialised before any multicast arrives
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();                          // prologue done; everything below touches memory of the preceding kernels
 
   const int crank = MC ? (int)cluster_ctarank() : 0;
   const int total_work = t.total_units;
@@ -450,17 +452,20 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     CLG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_K, B_K, MC, EPI>, ta, tb, tc, tx, t, e),
                 "cudaLaunchKernelEx(gemm_tc, cluster 2)");
     return check_launch("gemm_tc_kernel(mc)");
   }
   t.total_units = t.num_m * t.num_n * t.splits;
   const int grid = t.total_units < sms ? t.total_units : sms;
-  gemm_tc_kernel<BN, A_K, B_K, MC, EPI><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, tx, t, e);
+  CLG_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, A_K, B_K, MC, EPI>, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, tc, tx, t, e),
+              "launch(gemm_tc)");
   return check_launch("gemm_tc_kernel");
 }
 

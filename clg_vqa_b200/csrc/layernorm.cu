@@ -43,6 +43,8 @@ __device__ __forceinline__ float4 drop4(const Drop& d, uint64_t idx, float4 v) {
 template <int C4>
 __global__ void __launch_bounds__(LN_THREADS)
 ln_fwd_vec_kernel(const clgLayerNormFwdParams p, const Drop drop) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int N = 128 * C4;
   const float invN = 1.0f / (float)N;
@@ -102,6 +104,8 @@ template <int C4>
 __global__ void __launch_bounds__(LN_THREADS, 2)
 ln_bwd_vec_kernel(const clgLayerNormBwdParams p, const Drop drop_out, const Drop drop_in) {
   extern __shared__ float4 sm4[];
+  pdl_trigger();
+  pdl_wait();
   constexpr int N = 128 * C4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // smem: gamma [N] | per-warp accumulators [LN_WARPS][3][N] (only the arrays that are needed)
@@ -270,7 +274,7 @@ static int launch_bwd_vec(const clgLayerNormBwdParams& p, const Drop& dout, cons
     CLG_CUDA_OK(cudaFuncSetAttribute(ln_bwd_vec_kernel<C4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ln_bwd smem");
     configured = smem;
   }
-  ln_bwd_vec_kernel<C4><<<grid, LN_THREADS, smem, s>>>(p, dout, din);
+  CLG_CUDA_OK(launch_pdl(ln_bwd_vec_kernel<C4>, dim3(grid), dim3(LN_THREADS), smem, s, p, dout, din), "launch(ln_bwd_vec)");
   return check_launch("ln_bwd_vec_kernel");
 }
 
@@ -292,9 +296,9 @@ extern "C" int clg_layernorm_fwd(const clgLayerNormFwdParams* p, clgStream_t str
                    (!p->y || ((p->ldy % 4 == 0) && aligned16(p->y))) &&
                    (!p->y_lowp || ((p->ldy_lowp % 4 == 0) && aligned16(p->y_lowp))) &&
                    (!p->add_mat || ((p->ld_add % 4 == 0) && aligned16(p->add_mat))) && (!p->add_vec || aligned16(p->add_vec));
-  if (vec && p->N == 768) ln_fwd_vec_kernel<6><<<grid, LN_THREADS, 0, s>>>(*p, d);
-  else if (vec && p->N == 1536) ln_fwd_vec_kernel<12><<<grid, LN_THREADS, 0, s>>>(*p, d);
-  else if (vec && p->N == 128) ln_fwd_vec_kernel<1><<<grid, LN_THREADS, 0, s>>>(*p, d);
+  if (vec && p->N == 768) CLG_CUDA_OK(launch_pdl(ln_fwd_vec_kernel<6>, dim3(grid), dim3(LN_THREADS), 0, s, *p, d), "launch(ln_fwd)");
+  else if (vec && p->N == 1536) CLG_CUDA_OK(launch_pdl(ln_fwd_vec_kernel<12>, dim3(grid), dim3(LN_THREADS), 0, s, *p, d), "launch(ln_fwd)");
+  else if (vec && p->N == 128) CLG_CUDA_OK(launch_pdl(ln_fwd_vec_kernel<1>, dim3(grid), dim3(LN_THREADS), 0, s, *p, d), "launch(ln_fwd)");
   else ln_fwd_gen_kernel<<<grid, LN_THREADS, 0, s>>>(*p, d);
   return check_launch("ln_fwd_kernel");
 }

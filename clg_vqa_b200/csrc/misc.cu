@@ -70,6 +70,8 @@ template <> struct Vec8<float> {
 template <typename T>
 __global__ void colsum_vec_kernel(const T* __restrict__ x, int64_t ld, int M, int N, float* __restrict__ out, int rows_per_block) {
   __shared__ float red[8][256 + 8];
+  pdl_trigger();
+  pdl_wait();
   const int col = blockIdx.x * 256 + threadIdx.x * 8;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(M, r0 + rows_per_block);
@@ -228,8 +230,8 @@ extern "C" int clg_colsum(const void* x, int32_t dtype, int64_t ld, int32_t M, i
   const int rows_per_block = (M + row_blocks - 1) / row_blocks;
   dim3 grid(col_blocks, row_blocks), block(32, 8);
   if (vec) {
-    if (dtype == CLG_BF16) colsum_vec_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, ld, M, N, out, rows_per_block);
-    else colsum_vec_kernel<float><<<grid, block, 0, s>>>((const float*)x, ld, M, N, out, rows_per_block);
+    if (dtype == CLG_BF16) CLG_CUDA_OK(launch_pdl(colsum_vec_kernel<bf16>, grid, block, 0, s, (const bf16*)x, ld, M, N, out, rows_per_block), "launch(colsum)");
+    else CLG_CUDA_OK(launch_pdl(colsum_vec_kernel<float>, grid, block, 0, s, (const float*)x, ld, M, N, out, rows_per_block), "launch(colsum)");
   } else {
     if (dtype == CLG_BF16) colsum_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, ld, M, N, out, rows_per_block);
     else colsum_kernel<float><<<grid, block, 0, s>>>((const float*)x, ld, M, N, out, rows_per_block);
