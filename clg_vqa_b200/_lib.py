@@ -132,6 +132,7 @@ class AdamWParams(C.Structure):
         ("beta1", c_f32), ("beta2", c_f32), ("eps", c_f32),
         ("bias_c1", c_f32), ("bias_c2", c_f32), ("_pad", c_i32),
         ("shadow", c_vp), ("mask_bits", c_vp),
+        ("hot", c_vp),
     ]
 
 
@@ -164,7 +165,7 @@ SYMBOLS = {
     "clg_embed_text_fwd": (C.c_int, [C.POINTER(EmbedTextParams), c_vp]),
     "clg_embed_text_bwd": (C.c_int, [C.POINTER(EmbedTextBwdParams), c_vp]),
     "clg_gqa_prior_loss": (C.c_int, [C.POINTER(GqaLossParams), c_vp]),
-    "clg_sumsq": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp]),
+    "clg_sumsq": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "clg_adamw_step": (C.c_int, [C.POINTER(AdamWParams), c_vp]),
     "clg_cast_shadow": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "clg_cast_f32_to_bf16": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),

@@ -114,8 +114,7 @@ template <int EPI, int BN>
 struct FastEpi {
   using Cfg = EpiCfg<EPI>;
   static constexpr int CW = Cfg::CW;
-  static constexpr int NCH = BN / CW / 2;            // chunks per warp per tile (two warps share a lane quarter)
-  static_assert(NCH >= 1, "tile too narrow for the fast epilogue");
+  static_assert(BN / CW >= 3, "tile too narrow for the fast epilogue");
 
   const EpiArgs& e;
   const CUtensorMap* tm_c;

@@ -20,7 +20,10 @@ namespace clg {
 static constexpr int BM = 128;
 static constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
 static constexpr int UMMA_K = 16;
-static constexpr int NUM_THREADS = 320;  // 10 warps: TMA, MMA, 8 epilogue
+// warps: TMA producer, MMA issuer, then the epilogue warps (8; 12 for the ALU-heavy GeLU-pair epilogue, whose per-tile
+// work must fit under a K = 768 main loop)
+template <int EPI> __host__ __device__ constexpr int epi_warps() { return EPI == EPI_GELU_PAIR ? 12 : 8; }
+template <int EPI> __host__ __device__ constexpr int num_threads() { return 64 + 32 * epi_warps<EPI>(); }
 static constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KiB
 
 static constexpr int SMEM_MAX = 232448;            // 227 KiB per CTA
@@ -33,7 +36,7 @@ template <int BN, int EPI, int MC = 0> struct TileCfg {
   static constexpr int B_TILE_BYTES = (MC == 2 ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   // epilogue scratch: generic = one [32][33] fp32 staging tile per warp; fast = per-warp TMA boxes
-  static constexpr int EPI_BYTES = EPI == EPI_GENERIC ? 8 * STG_FLOATS * 4 : 8 * epi_warp_bytes<EPI>();
+  static constexpr int EPI_BYTES = EPI == EPI_GENERIC ? 8 * STG_FLOATS * 4 : epi_warps<EPI>() * epi_warp_bytes<EPI>();
   static constexpr int FIT = (SMEM_MAX - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
   static constexpr int KSTAGES = FIT > 8 ? 8 : FIT;
   static constexpr int TMEM_COLS = 2 * BN;          // power of two >= 32 for BN in {64,128,256}
@@ -53,7 +56,7 @@ struct TcArgs {
 // half of the shared B tile and TMA-multicasts it into both CTAs' shared memory (A 16 KiB + B/2 per k-block from
 // L2 instead of A + B), so the L2 -> SM traffic of the weight / activation tile is halved.
 template <int BN, bool A_K, bool B_K, int MC, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads<EPI>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_x,
                const TcArgs t, const EpiArgs e) {
@@ -73,7 +76,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * KSTAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * KSTAGES + 4);
   const uint32_t epi_in_bar = bar_base + 8u * (2 * KSTAGES + 5);
-  static_assert(8 * (2 * KSTAGES + 5 + 16) <= BAR_BYTES, "barrier area too small");
+  static_assert(8 * (2 * KSTAGES + 5 + 2 * 12) <= BAR_BYTES, "barrier area too small");
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + KSTAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES + 8 * (2 * KSTAGES + 4));
 
@@ -85,8 +88,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
     for (int s = 0; s < KSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), MC == 1 ? 2 : 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), MC == 2 ? 16 : 8); }
-    for (int s = 0; s < 16; ++s) mbar_init(epi_in_bar + 8u * s, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), (MC == 2 ? 2 : 1) * epi_warps<EPI>()); }
+    for (int s = 0; s < 2 * epi_warps<EPI>(); ++s) mbar_init(epi_in_bar + 8u * s, 1);
     if (EPI != EPI_GENERIC) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_c)) : "memory");
       if (EPI != EPI_PLAIN) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_x)) : "memory");
@@ -258,17 +261,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       // fast forms (splits == 1): this warp owns columns [half*BN/2, (half+1)*BN/2) of its 32-row slab and walks
       // them in 64 B chunks; `pos` numbers its chunks over all tiles (ring slots, barrier parities, prefetch)
       using FE = FastEpi<EPI, BN>;
-      constexpr int NCH = FE::NCH, CW = FE::CW, NIN = EpiCfg<EPI>::NIN;
+      constexpr int CW = FE::CW, NIN = EpiCfg<EPI>::NIN;
+      constexpr int NEW = epi_warps<EPI>(), PARTS = NEW / 4, NCHT = BN / CW;      // column parts per lane quarter, chunks per slab
       const int ew = warp - 2;
+      const int part = ew >> 2;
+      // chunks [c_first, c_first + nch) of the 32-row slab belong to this warp (parts differ by at most one chunk)
+      const int c_first = (part * NCHT) / PARTS;
+      const int nch = ((part + 1) * NCHT) / PARTS - c_first;
       const uint32_t wbase = epi_base + ew * epi_warp_bytes<EPI>();
       FE fe{e, &tma_c, &tma_x, wbase, wbase + NIN * EPI_BOX_BYTES, epi_in_bar + 16u * ew, lane, q, half};
       auto coords = [&](uint32_t pos, int& row0, int& col) -> bool {
-        const int lt = (int)(pos / NCH), ci = (int)(pos % NCH);
+        const int lt = (int)(pos / (uint32_t)nch), ci = (int)(pos % (uint32_t)nch);
         const int w = w_first + lt * w_step;
         if (w >= total_work) return false;
         const int n_blk = w % t.num_n, m_blk = m_block_of(w);
         row0 = m_blk * BM + q * 32;
-        col = n_blk * BN + (half * NCH + ci) * CW;
+        col = n_blk * BN + (c_first + ci) * CW;
         return true;
       };
       if (NIN > 0 && lane == 0) {
@@ -282,13 +290,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         mbar_wait(tfull_bar(as), aphase);
         __syncwarp();
         tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c_first * CW);
+        const int n_blk = w % t.num_n, m_blk = m_block_of(w);
+        const int row0 = m_blk * BM + q * 32;
+        const int col0 = n_blk * BN + c_first * CW;
 #pragma unroll 1
-        for (int ci = 0; ci < NCH; ++ci, ++pos) {
-          int row0, col, nrow0 = 0, ncol = 0;
-          coords(pos, row0, col);
+        for (int ci = 0; ci < nch; ++ci, ++pos) {
+          int nrow0 = 0, ncol = 0;
           const bool nv = NIN > 0 ? coords(pos + NIN, nrow0, ncol) : false;
-          fe.chunk(pos, taddr + (uint32_t)(ci * CW), row0, col, nv, nrow0, ncol);
+          fe.chunk(pos, taddr + (uint32_t)(ci * CW), row0, col0 + ci * CW, nv, nrow0, ncol);
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -449,7 +459,7 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
     const int clusters = t.total_units < max_clusters ? t.total_units : max_clusters;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(num_threads<EPI>());
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -464,7 +474,7 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
   }
   t.total_units = t.num_m * t.num_n * t.splits;
   const int grid = t.total_units < sms ? t.total_units : sms;
-  CLG_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, A_K, B_K, MC, EPI>, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, tc, tx, t, e),
+  CLG_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, A_K, B_K, MC, EPI>, dim3(grid), dim3(num_threads<EPI>()), Cfg::SMEM_BYTES, stream, ta, tb, tc, tx, t, e),
               "launch(gemm_tc)");
   return check_launch("gemm_tc_kernel");
 }
@@ -543,6 +553,9 @@ int gemm_tc(const clgGemmParams& p, cudaStream_t stream) {
   static const int force_bn = [] { const char* s = getenv("CLG_GEMM_FORCE_BN"); return s ? atoi(s) : 0; }();
   if (force_bn == 256 && p.N > 128) bn = 256;
   if (force_bn == 128 && p.N > 64) bn = 128;
+  // (A second launch with narrower units for the rows of the last, partial round was measured and dropped: the step is
+  // bound by L2 -> SM operand traffic when all SMs are busy, so the few clusters of a partial round run their units
+  // ~1.7x faster than a full round and the split gains nothing.)
   if (bn == 256) return dispatch_major<256>(p, e, stream);
   if (bn == 128) return dispatch_major<128>(p, e, stream);
   return dispatch_major<64>(p, e, stream);

@@ -12,17 +12,28 @@ static constexpr int CHUNK = 2048;
 static constexpr int OPT_THREADS = 256;   // 8 elements per thread per chunk
 
 __global__ void __launch_bounds__(256)
-sumsq_partial_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partials) {
+sumsq_partial_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partials, uint8_t* __restrict__ hot) {
+  // one warp per 256-element block (8 consecutive floats per lane): the block's "has a non-zero gradient" bit
+  // comes for free with the norm
   __shared__ float red[8];
   float acc = 0.f;
-  const int64_t n4 = n >> 2;
+  const int lane = threadIdx.x & 31;
+  const int64_t nblk = n >> 8;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const float4* g4 = reinterpret_cast<const float4*>(g);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 v = __ldg(g4 + i);
-    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  for (int64_t b = warp0; b < nblk; b += nwarps) {
+    const float4 v0 = __ldg(g4 + b * 64 + lane * 2);
+    const float4 v1 = __ldg(g4 + b * 64 + lane * 2 + 1);
+    acc += v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w + v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
+    if (hot) {
+      const bool nz = (v0.x != 0.f) | (v0.y != 0.f) | (v0.z != 0.f) | (v0.w != 0.f) | (v1.x != 0.f) | (v1.y != 0.f) |
+                      (v1.z != 0.f) | (v1.w != 0.f);
+      if (__any_sync(0xffffffffu, nz) && lane == 0) hot[b] = 1;
+    }
   }
   if (blockIdx.x == 0)
-    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) acc += g[i] * g[i];
+    for (int64_t i = (nblk << 8) + threadIdx.x; i < n; i += blockDim.x) acc += g[i] * g[i];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -64,13 +75,22 @@ adamw_kernel(const clgAdamWParams p) {
     const int64_t base = c * CHUNK + (int64_t)threadIdx.x * 8;
     const int64_t rel = base - tm.start;          // element offset inside the tensor
     if (rel >= tm.numel) continue;                // tail padding of the tensor's last chunk
+    const bool cold = UPDATE && p.hot && !p.hot[base >> 8];      // warp-uniform: a warp covers one 256-element block
+    if (cold && !(tm.wd > 0.f)) continue;                         // g = m = v = 0 and no decay: nothing changes
     float pv[8];
     {
       const float4 a = *reinterpret_cast<const float4*>(p.p + base);
       const float4 b = *reinterpret_cast<const float4*>(p.p + base + 4);
       pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w; pv[4] = b.x; pv[5] = b.y; pv[6] = b.z; pv[7] = b.w;
     }
-    if (UPDATE) {
+    if (cold) {
+      // the dense formulas with g = m = v = 0 reduce to the decoupled decay alone (bit-identical: p - step*(0/eps) == p)
+      const float decay = tm.lr * tm.wd;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pv[j] = pv[j] - decay * pv[j];
+      *reinterpret_cast<float4*>(p.p + base) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+      *reinterpret_cast<float4*>(p.p + base + 4) = make_float4(pv[4], pv[5], pv[6], pv[7]);
+    } else if (UPDATE) {
       float gv[8], mv[8], vv[8];
       {
         const float4 a = __ldg(reinterpret_cast<const float4*>(p.g + base));
@@ -124,7 +144,8 @@ adamw_kernel(const clgAdamWParams p) {
 
 }  // namespace clg
 
-extern "C" int clg_sumsq(const float* g, int64_t n, float* partials, int32_t num_partials, float* out, clgStream_t stream) {
+extern "C" int clg_sumsq(const float* g, int64_t n, float* partials, int32_t num_partials, float* out, uint8_t* hot,
+                         clgStream_t stream) {
   using namespace clg;
   if (!g || !partials || !out || n < 0 || num_partials <= 0) return CLG_ERR_ARG;
   int st = require_sm100();
@@ -132,7 +153,7 @@ extern "C" int clg_sumsq(const float* g, int64_t n, float* partials, int32_t num
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int grid = num_sms() * 4;
   if (grid > num_partials) grid = num_partials;
-  sumsq_partial_kernel<<<grid, 256, 0, s>>>(g, n, partials);
+  sumsq_partial_kernel<<<grid, 256, 0, s>>>(g, n, partials, hot);
   st = check_launch("sumsq_partial_kernel");
   if (st != CLG_OK) return st;
   sumsq_final_kernel<<<1, 256, 0, s>>>(partials, grid, out);

@@ -236,6 +236,9 @@ class Engine:
         from . import optim as _optim
         _optim.register_engine(self)
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=device)
+        # one byte per 256 arena elements: 1 = the block has received a non-zero gradient at some point (optim.py)
+        self._hot = torch.ones(self.p_flat.numel() // 256, dtype=torch.uint8, device=device)
+        self._hot_valid = False
 
     def _build_tables(self, lr_wd=None):
         """chunk -> tensor table and the clgTensorMeta array (lr / wd filled by the optimiser)."""
@@ -602,6 +605,7 @@ class Engine:
             raise ops.ClgError("backward called for a forward whose activations were overwritten by a later forward")
         with torch.no_grad():
             self._attach_grads()
+            self._hot_valid = False          # new gradients: the block marks are stale until the next norm pass
             dl = dlogits.contiguous().float()
             if self.family == "m3p":
                 self._backward_m3p(dl, sv)

@@ -56,7 +56,10 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0):
     if eng is None or float(norm_type) != 2.0:
         return torch.nn.utils.clip_grad_norm_(params, max_norm, norm_type)
     eng._sumsq.zero_()
-    ops.sumsq(eng.g_flat, eng._partials, eng._sumsq)
+    # the norm pass also marks which 256-element blocks of the gradient arena hold a non-zero (eng._hot); the fused
+    # AdamW of THIS gradient then skips the m / v traffic of blocks that have never received one
+    ops.sumsq(eng.g_flat, eng._partials, eng._sumsq, hot=eng._hot)
+    eng._hot_valid = True
     _PENDING_CLIP[id(eng)] = float(max_norm)
     return eng._sumsq.sqrt()
 
@@ -92,6 +95,8 @@ class AdamW(Optimizer):
             m = torch.zeros_like(eng.p_flat)
             v = torch.zeros_like(eng.p_flat)
             fs = dict(engine=eng, p_flat_ptr=eng.p_flat.data_ptr(), m=m, v=v, step=0)
+            eng._hot.zero_()          # fresh moments: every block is cold until it sees a gradient
+            eng._hot_valid = False
             # carry over per-parameter state created by an earlier load_state_dict
             for g in self.param_groups:
                 for p in g["params"]:
@@ -102,6 +107,7 @@ class AdamW(Optimizer):
                     vv = v[o:o + p.numel()].view(p.shape)
                     if st and "exp_avg" in st:
                         mv.copy_(st["exp_avg"]); vv.copy_(st["exp_avg_sq"])
+                        eng._hot.fill_(1)     # restored moments may be non-zero anywhere: dense updates
                         fs["step"] = max(fs["step"], int(st.get("step", 0)))
                     self.state[p] = {"step": fs["step"], "exp_avg": mv, "exp_avg_sq": vv}
             self._fused = fs
@@ -155,7 +161,9 @@ class AdamW(Optimizer):
                        max_norm=max_norm if max_norm is not None else 0.0, gscale=self.grad_scale,
                        beta1=b1, beta2=b2, eps=g0["eps"], bias_c1=c1, bias_c2=c2,
                        shadow=eng.shadow if eng.precision == "bf16" else None,
-                       mask_bits=eng.mask_bits if eng.has_masks else None)
+                       mask_bits=eng.mask_bits if eng.has_masks else None,
+                       hot=eng._hot if eng._hot_valid else None)
+        eng._hot_valid = False
         for p in self.state:
             self.state[p]["step"] = t
         if eng.precision == "bf16":
@@ -164,6 +172,10 @@ class AdamW(Optimizer):
             eng._shadow_versions = None
         eng.grads_consumed = True
         return loss
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._fused = None          # rebuilt on the next step from the restored per-parameter moments (dense updates)
 
     def zero_grad(self, set_to_none: bool = True):
         fs = self._fused

@@ -119,3 +119,20 @@ def test_fused_colsum_matches_separate(backend):
     bias = _rand(N, seed=24)
     ops.gemm(a, w, y, b_kmajor=False, bias=bias, colsum=cs2, backend=backend)
     assert _rel(cs2, (a.double() @ w.double() + bias.double()).sum(0)) < 1e-4
+
+
+def test_large_m_residual_dropout_all_rows():
+    """M = 19456, N = 768: several 256 x 256 units per persistent CTA pair plus a partial last round; values (hence the
+    dropout mask: a wrong mask changes values by O(1)) must agree with the SIMT backend on every row."""
+    M, N, K = 19456, 768, 1536
+    a = _rand(M, K, dtype=torch.bfloat16, seed=31)
+    w = _rand(N, K, dtype=torch.bfloat16, scale=0.05, seed=32)
+    bias = _rand(N, seed=33)
+    res = _rand(M, N, seed=34)
+    site = DropSite(0.1, seed=9, offset=5 << 20)
+    y = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(a, w, y, bias=bias, residual=res, dropout=site)
+    ref = torch.empty(M, N, device=DEV)
+    ops.gemm(a, w, ref, bias=bias, residual=res, dropout=site, backend=ops.GEMM_SIMT)
+    assert _rel(y, ref) < 2e-5
+    assert _rel(y[-300:], ref[-300:]) < 2e-5

@@ -84,3 +84,51 @@ def test_layernorm_generic_width(N):
     dx = torch.empty_like(x); dg = torch.zeros(N, device=DEV); db = torch.zeros(N, device=DEV)
     ops.layernorm_bwd(dy, x, g, mean, rstd, dx=dx, dgamma=dg, dbeta=db)
     assert _rel(dx, xr.grad) < 1e-5 and _rel(dg, gr.grad) < 1e-5 and _rel(db, br.grad) < 1e-5
+
+
+def test_adamw_cold_blocks_bit_identical_to_dense():
+    """Blocks of 256 elements that have never received a gradient (word-embedding rows no batch has touched) take the
+    shortcut p -= lr*wd*p; the result must be bit-identical to the dense update, and the norm pass must mark exactly
+    the blocks with non-zero gradients."""
+    import math
+    from clg_vqa_b200 import _lib as L
+    rows, dim = 4000, 768
+    k = rows * dim
+    n = (k + L.CHUNK - 1) // L.CHUNK * L.CHUNK + 2 * L.CHUNK
+    k2 = 1000                                    # a second, non-decayed tensor that never gets gradients
+    start2 = n - L.CHUNK
+    torch.manual_seed(3)
+    p0 = torch.zeros(n, device=DEV); p0[:k] = torch.randn(k, device=DEV) * 0.05; p0[start2:start2 + k2] = 1.0
+    chunk_tensor = torch.full((n // L.CHUNK,), -1, dtype=torch.int32)
+    chunk_tensor[:(k + L.CHUNK - 1) // L.CHUNK] = 0
+    chunk_tensor[start2 // L.CHUNK] = 1
+    metas = (L.TensorMeta * 2)()
+    metas[0] = L.TensorMeta(4e-5, 1e-4, 0, -1, 0, k)
+    metas[1] = L.TensorMeta(4e-5, 0.0, -1, -1, start2, k2)
+    chunk_tensor = chunk_tensor.to(DEV)
+    tens = torch.frombuffer(bytearray(bytes(metas)), dtype=torch.uint8).to(DEV)
+    state = {}
+    for mode in ("dense", "hot"):
+        p = p0.clone(); m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV)
+        shadow = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
+        hot = torch.zeros(n // 256, device=DEV, dtype=torch.uint8)
+        partials = torch.zeros(1024, device=DEV); ss = torch.zeros(1, device=DEV)
+        gen = torch.Generator(device="cpu").manual_seed(11)
+        touched = torch.zeros(rows, dtype=torch.bool)
+        for step in range(1, 5):
+            g = torch.zeros(n, device=DEV)
+            ids = torch.randperm(rows, generator=gen)[:150]          # unique: index_put with duplicates is not deterministic
+            touched[ids] = True
+            g.view(-1)[:k].view(rows, dim)[ids.to(DEV)] = torch.randn(150, dim, generator=gen).to(DEV)
+            ss.zero_()
+            ops.sumsq(g, partials, ss, hot=hot if mode == "hot" else None)
+            ops.adamw_step(p, g, m, v, chunk_tensor, tens, sumsq=ss, max_norm=1.0, eps=1e-6, bias_c1=1 - 0.9 ** step,
+                           bias_c2=1 - 0.999 ** step, shadow=shadow, hot=hot if mode == "hot" else None)
+        state[mode] = (p, m, v, shadow, hot, touched)
+    for a, b in zip(state["dense"][:4], state["hot"][:4]):
+        assert torch.equal(a, b)
+    hot, touched = state["hot"][4], state["hot"][5]
+    assert torch.equal(hot[:k // 256].view(rows, 3).bool().cpu(), touched[:, None].expand(rows, 3))
+    assert int(hot[k // 256:].sum()) == 0
+    assert 0.05 < float(touched.float().mean()) < 0.5           # the test exercises both paths
+    assert torch.equal(state["hot"][0][start2:start2 + k2], torch.ones(k2, device=DEV))
