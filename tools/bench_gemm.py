@@ -48,4 +48,7 @@ run(19456, 768, 3072, name="FFN2 shape, plain bf16")
 run(19456, 768, 3072, cdt=torch.float32, bias=False, name="FFN2 shape, generic f32")
 run(19456, 768, 768, cdt=torch.float32, res=True, name="out-proj (+res fp32)")
 run(2304, 768, 19456, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="QKV wgrad")
+run(3072, 768, 19456, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="FFN1 wgrad")
+run(768, 3072, 19456, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="FFN2 wgrad")
+run(768, 768, 19456, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="out-proj wgrad")
 run(19456, 768, 2304, b_k=False, cdt=torch.float32, res=True, bias=False, name="QKV dgrad (+res)")
