@@ -78,6 +78,7 @@ class AttentionFwdParams(C.Structure):
         ("ctx", c_vp), ("ld_ctx", c_i64), ("lse", c_vp),
         ("dtype", c_i32), ("B", c_i32), ("S", c_i32), ("H", c_i32),
         ("scale", c_f32), ("_pad", c_i32), ("dropout", Dropout),
+        ("cu_rows", c_vp), ("total_rows", c_i32), ("_pad2", c_i32),
     ]
 
 
@@ -88,6 +89,7 @@ class AttentionBwdParams(C.Structure):
         ("lse", c_vp), ("dqkv", c_vp), ("ld_dqkv", c_i64),
         ("dtype", c_i32), ("B", c_i32), ("S", c_i32), ("H", c_i32),
         ("scale", c_f32), ("_pad", c_i32), ("dropout", Dropout),
+        ("cu_rows", c_vp), ("total_rows", c_i32), ("_pad2", c_i32),
     ]
 
 
@@ -169,6 +171,9 @@ SYMBOLS = {
     "clg_adamw_step": (C.c_int, [C.POINTER(AdamWParams), c_vp]),
     "clg_cast_shadow": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "clg_cast_f32_to_bf16": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "clg_pack_index": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int32, C.c_int32, c_vp, c_vp, c_vp]),
+    "clg_rows_gather": (C.c_int, [c_vp, c_i64, c_vp, C.c_int32, c_vp, c_i64, C.c_int32, C.c_int32, c_vp]),
+    "clg_rows_scatter": (C.c_int, [c_vp, c_i64, c_vp, C.c_int32, c_vp, c_i64, C.c_int32, C.c_int32, c_vp]),
     "clg_cast_f32_to_bf16_2d": (C.c_int, [c_vp, c_i64, c_vp, c_i64, C.c_int32, C.c_int32, c_vp]),
     "clg_pack_mask": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "clg_apply_mask": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),

@@ -281,9 +281,11 @@ extern "C" int clg_attention_fwd(const clgAttentionFwdParams* p, clgStream_t str
       st = attention_pipe_fwd(*p, s);
       if (st != CLG_ERR_UNSUPPORTED) return st;
     }
+    if (p->cu_rows) return CLG_ERR_UNSUPPORTED;     // only the pipelined kernels read the packed layout
     st = attention_tc_fwd(*p, s);
     if (st != CLG_ERR_UNSUPPORTED) return st;
   }
+  if (p->cu_rows) return CLG_ERR_UNSUPPORTED;
   const size_t smem = fwd_smem(p->S);
   const Drop d = make_drop(p->dropout);
   dim3 grid(p->H, p->B);
@@ -312,9 +314,11 @@ extern "C" int clg_attention_bwd(const clgAttentionBwdParams* p, clgStream_t str
       st = attention_pipe_bwd(*p, s);
       if (st != CLG_ERR_UNSUPPORTED) return st;
     }
+    if (p->cu_rows) return CLG_ERR_UNSUPPORTED;
     st = attention_tc_bwd(*p, s);
     if (st != CLG_ERR_UNSUPPORTED) return st;
   }
+  if (p->cu_rows) return CLG_ERR_UNSUPPORTED;
   const size_t smem = bwd_smem(p->S);
   const Drop d = make_drop(p->dropout);
   dim3 grid(p->H, p->B);

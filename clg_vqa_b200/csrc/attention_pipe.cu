@@ -28,6 +28,10 @@ struct AttnPipeArgs {
   const float* key_bias;                  // [B, S]
   float* lse;                             // [B, H, S]
   Drop drop;
+  // packed variable-length layout (optional): sample b owns rows [cu[b], cu[b+1]); outputs are then written row by row
+  // (a TMA box of fixed height would spill into the next sample)
+  const int32_t* cu;
+  bf16* out; int64_t ld_out;              // ctx (forward) / dqkv (backward), used by the varlen stores
 };
 
 __device__ __forceinline__ uint32_t psw_off(int row, int col /*0..63*/) {       // SWIZZLE_128B, 128 B rows
@@ -121,13 +125,14 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       const int w = (int)blockIdx.x + it * (int)gridDim.x;
       const int s = it % NST;
       mbar_wait(bar(PB_EMPTY + s), ((it / NST) & 1) ^ 1u);
+      const int b = w / H, h = w % H;
+      const int row0 = a.cu ? __ldg(a.cu + b) : b * S;
       if (elect_one()) {
-        const int b = w / H, h = w % H;
         const uint32_t st = sStage + (uint32_t)s * 3u * TN;
         mbar_expect_tx(bar(PB_FULL + s), 3u * TN);
-        tma_load_2d(st, &tm_qkv, bar(PB_FULL + s), h * PD, b * S);
-        tma_load_2d(st + TN, &tm_qkv, bar(PB_FULL + s), H * PD + h * PD, b * S);
-        tma_load_2d(st + 2 * TN, &tm_qkv, bar(PB_FULL + s), 2 * H * PD + h * PD, b * S);
+        tma_load_2d(st, &tm_qkv, bar(PB_FULL + s), h * PD, row0);
+        tma_load_2d(st + TN, &tm_qkv, bar(PB_FULL + s), H * PD + h * PD, row0);
+        tma_load_2d(st + 2 * TN, &tm_qkv, bar(PB_FULL + s), 2 * H * PD + h * PD, row0);
       }
       __syncwarp();
     }
@@ -181,9 +186,7 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const int wq = warp & 3;                       // TMEM lane quarter of this warp
     const int row = wq * 32 + lane;                // query row == TMEM lane
     const int tg = (warp - 2 - 4 * g) * 32 + lane; // thread index inside the group
-    const bool valid = row < S;
     const bool in_tile = row < NP;
-    const bool warp_live = wq * 32 < S;
     float* kb = kbuf + g * 128;                    // key bias * log2(e)
     const uint32_t sP = sP0 + (uint32_t)g * KB * TN;
     uint8_t* gP = gen + (sP - base);
@@ -192,16 +195,26 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const uint32_t trow = tmem + (uint32_t)(g * TG) + ((uint32_t)(wq * 32) << 16);
     const float scale2 = a.scale * LOG2E;          // softmax in base 2: p = 2^(s * scale * log2e + kb * log2e - m)
     const bool even_rows = (S & 1) == 0;           // every row's first dropout index is even: pairwise hashing
+    // rows of an item: [row0, row0 + Sb) of the (possibly packed) token dimension
+    auto item_rows = [&](int it, int& row0, int& Sb) {
+      const int b = ((int)blockIdx.x + it * (int)gridDim.x) / H;
+      if (a.cu) { row0 = __ldg(a.cu + b); Sb = __ldg(a.cu + b + 1) - row0; } else { row0 = b * S; Sb = S; }
+    };
     auto load_kb = [&](int it) -> float {
-      if (it >= n_it || tg >= S) return -INFINITY;
-      const int w = (int)blockIdx.x + it * (int)gridDim.x;
-      return __ldg(a.key_bias + (int64_t)(w / H) * S + tg) * LOG2E;
+      if (it >= n_it) return -INFINITY;
+      int r0, sb;
+      item_rows(it, r0, sb);
+      return tg < sb ? __ldg(a.key_bias + (int64_t)r0 + tg) * LOG2E : -INFINITY;
     };
     float kb_next = load_kb(g);
     for (int it = g; it < n_it; it += NG) {
       const int u = it / NG;
       const int w = (int)blockIdx.x + it * (int)gridDim.x;
       const int b = w / H, h = w % H;
+      int row0, Sb;
+      item_rows(it, row0, Sb);
+      const bool valid = row < Sb;
+      const bool warp_live = wq * 32 < Sb;
       const float kbv = kb_next;
       kb_next = load_kb(it + NG);                  // in flight during this item
       if (tg == 0) bulk_wait_read<0>();            // the previous TMA store has read the O staging tile
@@ -271,19 +284,29 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         tmem_wait_ld_dep32(o);
         tmem_wait_ld_dep32(o + 32);
         if (valid) {
+          if (a.cu) {             // packed layout: this row's 128 B straight to global
+            uint4* og = reinterpret_cast<uint4*>(a.out + (int64_t)(row0 + row) * a.ld_out + h * PD);
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(gO + psw_off(row, 8 * j)) =
-                make_uint4(pk2(o[8 * j + 0], o[8 * j + 1]), pk2(o[8 * j + 2], o[8 * j + 3]), pk2(o[8 * j + 4], o[8 * j + 5]),
-                           pk2(o[8 * j + 6], o[8 * j + 7]));
+            for (int j = 0; j < 8; ++j)
+              og[j] = make_uint4(pk2(o[8 * j + 0], o[8 * j + 1]), pk2(o[8 * j + 2], o[8 * j + 3]), pk2(o[8 * j + 4], o[8 * j + 5]),
+                                 pk2(o[8 * j + 6], o[8 * j + 7]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(gO + psw_off(row, 8 * j)) =
+                  make_uint4(pk2(o[8 * j + 0], o[8 * j + 1]), pk2(o[8 * j + 2], o[8 * j + 3]), pk2(o[8 * j + 4], o[8 * j + 5]),
+                             pk2(o[8 * j + 6], o[8 * j + 7]));
+          }
         }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(PB_TFREE + g));
-      fence_proxy_async();
-      named_bar(1 + g, 128);
-      if (tg == 0) { tma_store_2d(&tm_ctx, sO, h * PD, b * S); bulk_commit(); }
+      if (!a.cu) {
+        fence_proxy_async();
+        named_bar(1 + g, 128);
+        if (tg == 0) { tma_store_2d(&tm_ctx, sO, h * PD, row0); bulk_commit(); }
+      }
     }
     if (tg == 0) bulk_wait_all();
   }
@@ -346,15 +369,16 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       const int w = (int)blockIdx.x + it * (int)gridDim.x;
       const int s = it % NST;
       mbar_wait(bar(PB_EMPTY + s), ((it / NST) & 1) ^ 1u);
+      const int b = w / H, h = w % H;
+      const int row0 = a.cu ? __ldg(a.cu + b) : b * S;
       if (elect_one()) {
-        const int b = w / H, h = w % H;
         const uint32_t st = sStage + (uint32_t)s * 5u * TN;
         mbar_expect_tx(bar(PB_FULL + s), 5u * TN);
-        tma_load_2d(st, &tm_qkv, bar(PB_FULL + s), h * PD, b * S);
-        tma_load_2d(st + TN, &tm_qkv, bar(PB_FULL + s), H * PD + h * PD, b * S);
-        tma_load_2d(st + 2 * TN, &tm_qkv, bar(PB_FULL + s), 2 * H * PD + h * PD, b * S);
-        tma_load_2d(st + 3 * TN, &tm_do, bar(PB_FULL + s), h * PD, b * S);
-        tma_load_2d(st + 4 * TN, &tm_o, bar(PB_FULL + s), h * PD, b * S);
+        tma_load_2d(st, &tm_qkv, bar(PB_FULL + s), h * PD, row0);
+        tma_load_2d(st + TN, &tm_qkv, bar(PB_FULL + s), H * PD + h * PD, row0);
+        tma_load_2d(st + 2 * TN, &tm_qkv, bar(PB_FULL + s), 2 * H * PD + h * PD, row0);
+        tma_load_2d(st + 3 * TN, &tm_do, bar(PB_FULL + s), h * PD, row0);
+        tma_load_2d(st + 4 * TN, &tm_o, bar(PB_FULL + s), h * PD, row0);
       }
       __syncwarp();
     }
@@ -417,7 +441,6 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const int wq = warp & 3;
     const int row = wq * 32 + lane;
     const int tg = (warp - 2 - 4 * g) * 32 + lane;
-    const bool valid = row < S;
     const bool in_tile = row < NP;
     const bool warp_live = wq * 32 < NP;
     float* kb = kbuf + g * 128;
@@ -428,13 +451,19 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const float scale = a.scale;
     const float scale2 = a.scale * LOG2E;
     const bool even_rows = (S & 1) == 0;
+    auto item_rows = [&](int it, int& row0, int& Sb) {
+      const int b = ((int)blockIdx.x + it * (int)gridDim.x) / H;
+      if (a.cu) { row0 = __ldg(a.cu + b); Sb = __ldg(a.cu + b + 1) - row0; } else { row0 = b * S; Sb = S; }
+    };
     float kb_next = -INFINITY, lse_next = 0.f;
     auto load_next = [&](int it) {
       kb_next = -INFINITY; lse_next = 0.f;
       if (it >= n_it) return;
       const int w = (int)blockIdx.x + it * (int)gridDim.x;
-      if (tg < S) kb_next = __ldg(a.key_bias + (int64_t)(w / H) * S + tg) * LOG2E;
-      if (valid) lse_next = __ldg(a.lse + ((int64_t)w) * S + row);      // w = b * H + h
+      int r0, sb;
+      item_rows(it, r0, sb);
+      if (tg < sb) kb_next = __ldg(a.key_bias + (int64_t)r0 + tg) * LOG2E;
+      if (row < sb) lse_next = __ldg(a.lse + ((int64_t)w) * S + row);      // w = b * H + h
     };
     load_next(g);
     for (int it = g; it < n_it; it += 2) {
@@ -442,6 +471,9 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       const int s = it % NST;
       const int w = (int)blockIdx.x + it * (int)gridDim.x;
       const int b = w / H, h = w % H;
+      int row0, Sb;
+      item_rows(it, row0, Sb);
+      const bool valid = row < Sb;
       const float kbv = kb_next, lse_i = lse_next;
       load_next(it + 2);                           // in flight during this item
       if (tg == 0) bulk_wait_read<0>();            // the previous dQ/dK/dV stores have read the staging tiles
@@ -530,7 +562,7 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       mbar_wait(bar(PB_ORDY + g), u & 1);          // dV, dK, dQ in TMEM; P / dS tiles are free again
       __syncwarp();
       tcgen05_fence_after();
-      if (wq * 32 < S) {
+      if (wq * 32 < Sb) {
         // staging: dQ -> P block 0, dK -> P block 1, dV -> dS block 0 (S rows x 128 B each)
         uint8_t* stg[3] = {gP, gP + TN, gdS};
         const uint32_t src[3] = {tbase + 128, tbase + 64, tbase};
@@ -544,24 +576,34 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           tmem_wait_ld_dep32(o + 32);
           if (valid) {
             const float sc = mul[which];
+            if (a.cu) {           // packed layout: row-wise stores (which-th third of the dqkv row, head h)
+              uint4* og = reinterpret_cast<uint4*>(a.out + (int64_t)(row0 + row) * a.ld_out + which * ab.Hd + h * PD);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(stg[which] + psw_off(row, 8 * j)) =
-                  make_uint4(pk2(o[8 * j + 0] * sc, o[8 * j + 1] * sc), pk2(o[8 * j + 2] * sc, o[8 * j + 3] * sc),
-                             pk2(o[8 * j + 4] * sc, o[8 * j + 5] * sc), pk2(o[8 * j + 6] * sc, o[8 * j + 7] * sc));
+              for (int j = 0; j < 8; ++j)
+                og[j] = make_uint4(pk2(o[8 * j + 0] * sc, o[8 * j + 1] * sc), pk2(o[8 * j + 2] * sc, o[8 * j + 3] * sc),
+                                   pk2(o[8 * j + 4] * sc, o[8 * j + 5] * sc), pk2(o[8 * j + 6] * sc, o[8 * j + 7] * sc));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(stg[which] + psw_off(row, 8 * j)) =
+                    make_uint4(pk2(o[8 * j + 0] * sc, o[8 * j + 1] * sc), pk2(o[8 * j + 2] * sc, o[8 * j + 3] * sc),
+                               pk2(o[8 * j + 4] * sc, o[8 * j + 5] * sc), pk2(o[8 * j + 6] * sc, o[8 * j + 7] * sc));
+            }
           }
         }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(PB_TFREE + g));
-      fence_proxy_async();
-      named_bar(1 + g, 128);
-      if (tg == 0) {
-        tma_store_2d(&tm_dqkv, sP, h * PD, b * S);
-        tma_store_2d(&tm_dqkv, sP + TN, ab.Hd + h * PD, b * S);
-        tma_store_2d(&tm_dqkv, sdS, 2 * ab.Hd + h * PD, b * S);
-        bulk_commit();
+      if (!a.cu) {
+        fence_proxy_async();
+        named_bar(1 + g, 128);
+        if (tg == 0) {
+          tma_store_2d(&tm_dqkv, sP, h * PD, row0);
+          tma_store_2d(&tm_dqkv, sP + TN, ab.Hd + h * PD, row0);
+          tma_store_2d(&tm_dqkv, sdS, 2 * ab.Hd + h * PD, row0);
+          bulk_commit();
+        }
       }
     }
     if (tg == 0) bulk_wait_all();
@@ -628,7 +670,8 @@ int attention_pipe_fwd(const clgAttentionFwdParams& p, cudaStream_t stream) {
   if (fwd_pipe_smem(NP, nst, ng) > P_SMEM_MAX) return CLG_ERR_UNSUPPORTED;
   if ((p.ld_ctx * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(p.ctx) & 15)) return CLG_ERR_UNSUPPORTED;
   CUtensorMap tq, tc;
-  const int64_t rows = (int64_t)p.B * p.S;
+  if (p.cu_rows && p.total_rows <= 0) return CLG_ERR_ARG;
+  const int64_t rows = p.cu_rows ? (int64_t)p.total_rows : (int64_t)p.B * p.S;   // rows beyond are zero-filled by TMA
   int st = make_tmap_rows(&tq, p.qkv, 3LL * p.H * PD, rows, p.ld_qkv, NP);
   if (st != CLG_OK) return st;
   st = make_tmap_rows(&tc, p.ctx, (int64_t)p.H * PD, rows, p.ld_ctx, p.S);
@@ -638,6 +681,7 @@ int attention_pipe_fwd(const clgAttentionFwdParams& p, cudaStream_t stream) {
   a.B = p.B; a.S = p.S; a.H = p.H; a.NP = NP; a.items = p.B * p.H; a.nst = nst;
   a.scale = p.scale; a.key_bias = p.key_bias; a.lse = p.lse;
   a.drop = make_drop(p.dropout);
+  a.cu = p.cu_rows; a.out = (bf16*)p.ctx; a.ld_out = p.ld_ctx;
   const int smem = fwd_pipe_smem(NP, nst, ng);
   switch (NP / 16) {
     case 1: return launch_pipe_fwd<1>(tq, tc, a, smem, stream);
@@ -659,7 +703,8 @@ int attention_pipe_bwd(const clgAttentionBwdParams& p, cudaStream_t stream) {
   if (bwd_pipe_smem(NP, nst) > P_SMEM_MAX) return CLG_ERR_UNSUPPORTED;
   if ((p.ld_dqkv * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(p.dqkv) & 15)) return CLG_ERR_UNSUPPORTED;
   CUtensorMap tq, tdo, to, tdq;
-  const int64_t rows = (int64_t)p.B * p.S;
+  if (p.cu_rows && p.total_rows <= 0) return CLG_ERR_ARG;
+  const int64_t rows = p.cu_rows ? (int64_t)p.total_rows : (int64_t)p.B * p.S;
   int st = make_tmap_rows(&tq, p.qkv, 3LL * p.H * PD, rows, p.ld_qkv, NP);
   if (st != CLG_OK) return st;
   st = make_tmap_rows(&tdo, p.dctx, (int64_t)p.H * PD, rows, p.ld_dctx, NP);
@@ -674,6 +719,7 @@ int attention_pipe_bwd(const clgAttentionBwdParams& p, cudaStream_t stream) {
   a.B = p.B; a.S = p.S; a.H = p.H; a.NP = NP; a.items = p.B * p.H; a.nst = nst;
   a.scale = p.scale; a.key_bias = p.key_bias; a.lse = const_cast<float*>(p.lse);
   a.drop = make_drop(p.dropout);
+  a.cu = p.cu_rows; a.out = (bf16*)p.dqkv; a.ld_out = p.ld_dqkv;
   ab.Hd = p.H * PD;
   const int smem = bwd_pipe_smem(NP, nst);
   switch (NP / 16) {

@@ -30,6 +30,57 @@ __global__ void cast_f32_bf16_2d_kernel(const float* __restrict__ src, int64_t l
   }
 }
 
+// one CTA: per-sample kept-row counts -> exclusive scan -> packed-row -> source-row table
+__global__ void __launch_bounds__(1024)
+pack_index_kernel(const int64_t* __restrict__ tm, const int64_t* __restrict__ im, int B, int T, int R,
+                  int32_t* __restrict__ cu, int32_t* __restrict__ src) {
+  extern __shared__ int32_t cnt[];            // [B + 1]
+  const int S = T + R;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int c = 0;
+    for (int s = 0; s < S; ++s) {
+      const bool keep = (s == 0) || (s < T ? tm[(int64_t)b * T + s] != 0 : im[(int64_t)b * R + (s - T)] != 0);
+      c += keep ? 1 : 0;
+    }
+    cnt[b] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {                     // B is a few hundred: a serial scan is a microsecond
+    int run = 0;
+    for (int b = 0; b < B; ++b) { const int c = cnt[b]; cnt[b] = run; run += c; }
+    cnt[B] = run;
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b <= B; b += blockDim.x) cu[b] = cnt[b];
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int o = cnt[b];
+    for (int s = 0; s < S; ++s) {
+      const bool keep = (s == 0) || (s < T ? tm[(int64_t)b * T + s] != 0 : im[(int64_t)b * R + (s - T)] != 0);
+      if (keep) src[o++] = b * S + s;
+    }
+  }
+}
+
+// one warp per row; 16 B lanes when the row is 16 B-granular, scalar otherwise
+template <bool SCATTER>
+__global__ void rows_move_kernel(const uint8_t* __restrict__ src, int64_t ld_src_b, const int32_t* __restrict__ idx, int n,
+                                 uint8_t* __restrict__ dst, int64_t ld_dst_b, int row_bytes) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool vec = (row_bytes % 16 == 0) && (ld_src_b % 16 == 0) && (ld_dst_b % 16 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  for (int64_t i = w0; i < n; i += nw) {
+    const int64_t j = idx[i];
+    const uint8_t* s = src + (SCATTER ? i : j) * ld_src_b;
+    uint8_t* d = dst + (SCATTER ? j : i) * ld_dst_b;
+    if (vec) {
+      for (int o = lane * 16; o < row_bytes; o += 512) *reinterpret_cast<uint4*>(d + o) = __ldg(reinterpret_cast<const uint4*>(s + o));
+    } else {
+      for (int o = lane * 4; o < row_bytes; o += 128) *reinterpret_cast<uint32_t*>(d + o) = *reinterpret_cast<const uint32_t*>(s + o);
+    }
+  }
+}
+
 __global__ void pack_mask_kernel(const float* __restrict__ mask, uint32_t* __restrict__ bits, int64_t n) {
   // one warp packs 32 consecutive elements into one word with a ballot
   const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -192,6 +243,40 @@ extern "C" int clg_cast_f32_to_bf16_2d(const float* src, int64_t ld_src, void* d
   cast_f32_bf16_2d_kernel<<<ew_grid((int64_t)rows * ld_dst, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, ld_src, (bf16*)dst, ld_dst, rows, cols);
   return check_launch("cast_f32_bf16_2d_kernel");
+}
+
+extern "C" int clg_pack_index(const int64_t* txt_mask, const int64_t* img_mask, int32_t B, int32_t T, int32_t R,
+                              int32_t* cu_rows, int32_t* src_rows, clgStream_t stream) {
+  using namespace clg;
+  if (!txt_mask || !img_mask || !cu_rows || !src_rows || B <= 0 || B > 8192 || T < 1 || R < 0) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  pack_index_kernel<<<1, 1024, (B + 1) * sizeof(int32_t), static_cast<cudaStream_t>(stream)>>>(txt_mask, img_mask, B, T, R, cu_rows, src_rows);
+  return check_launch("pack_index_kernel");
+}
+
+static int rows_move(bool scatter, const void* src, int64_t ld_src, const int32_t* idx, int32_t n, void* dst, int64_t ld_dst,
+                     int32_t cols, int32_t dtype, clgStream_t stream) {
+  using namespace clg;
+  if (!src || !idx || !dst || n < 0 || cols <= 0) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  if (n == 0) return CLG_OK;
+  const int esz = dtype == CLG_BF16 ? 2 : 4;
+  if ((cols * esz) % 4 != 0) return CLG_ERR_UNSUPPORTED;
+  const int grid = ew_grid((int64_t)n * 32, 256);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (scatter) rows_move_kernel<true><<<grid, 256, 0, s>>>((const uint8_t*)src, ld_src * esz, idx, n, (uint8_t*)dst, ld_dst * esz, cols * esz);
+  else rows_move_kernel<false><<<grid, 256, 0, s>>>((const uint8_t*)src, ld_src * esz, idx, n, (uint8_t*)dst, ld_dst * esz, cols * esz);
+  return check_launch("rows_move_kernel");
+}
+extern "C" int clg_rows_gather(const void* src, int64_t ld_src, const int32_t* idx, int32_t n, void* dst, int64_t ld_dst,
+                               int32_t cols, int32_t dtype, clgStream_t stream) {
+  return rows_move(false, src, ld_src, idx, n, dst, ld_dst, cols, dtype, stream);
+}
+extern "C" int clg_rows_scatter(const void* src, int64_t ld_src, const int32_t* idx, int32_t n, void* dst, int64_t ld_dst,
+                                int32_t cols, int32_t dtype, clgStream_t stream) {
+  return rows_move(true, src, ld_src, idx, n, dst, ld_dst, cols, dtype, stream);
 }
 
 extern "C" int clg_pack_mask(const float* mask, uint32_t* bits, int64_t n, clgStream_t stream) {

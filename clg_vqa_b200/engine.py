@@ -15,6 +15,8 @@ are bf16 - the rounding points of the bf16 oracle.
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Dict, List, Optional
 
@@ -85,6 +87,7 @@ class Engine:
         self.base_seed = 0x5EED
         self.step_counter = 0
         self.grads_consumed = True       # True: next backward zeroes the gradient arena first
+        self.pack_enabled = os.environ.get("CLG_PACK", "1") != "0"   # drop masked positions before the encoder layers
         self.dp = None                   # optional parallel.GradExchange
         self.L = cfgmod.num_encoder_layers(self.cfg)
         self.d = self.cfg.hidden_size
@@ -408,6 +411,12 @@ class Engine:
             ws[k] = E(Mr)
         ws["x0"] = E(M, d)
         ws["x0_lp"] = E(M, d, dtype=lp) if lp != f32 else ws["x0"]
+        if lp != f32:
+            # packed joint sequence (masked positions dropped after the embeddings, see _forward)
+            ws["cu"] = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+            ws["src"] = torch.zeros(M, dtype=torch.int32, device=dev)
+            ws["xp"] = E(M, d); ws["xp_lp"] = E(M, d, dtype=lp); ws["kbp"] = E(M, 1)
+            ws["xfirst"] = E(B, d, dtype=lp)
         nslots = self.L if training else 1
         layers = []
         for _ in range(nslots):
@@ -440,6 +449,8 @@ class Engine:
             ws["ds"] = E(Mr, d); ws["dg"] = E(Mr, d, dtype=lp); ws["dl"] = E(Mr, d, dtype=lp)
             ws["dpre"] = E(B, P)
             ws["dpre_lp"] = E(B, P, dtype=lp) if lp != f32 else ws["dpre"]
+            if lp != f32:
+                ws["dxfirst"] = E(B, d); ws["dxd"] = E(M, d)
             for task, hw in heads.items():
                 hw["dhln"] = E(B, hw["C"]); hw["dhc"] = E(B, hw["C"])
                 if lp != f32:
@@ -528,44 +539,70 @@ class Engine:
                           y_lowp=ws["x0_lp"] if bf else None, mean=ws["m_v"], rstd=ws["r_v"],
                           out_map=rowmap(R, T, S), dropout=self._site(1, p_h, training))
         # ---- encoder layers
-        x, x_lp = ws["x0"], ws["x0_lp"]
+        x, x_lp, kb = ws["x0"], ws["x0_lp"], ws["kb"]
+        # Packing: masked positions (text padding, missing regions) are dropped before the encoder.  Exact: their key
+        # bias (-10000) makes exp() underflow to 0 for every kept query, nothing downstream reads their outputs (the
+        # pooler takes token 0, which is always kept) and hence their gradients vanish identically.  The layers then run
+        # on Mp = sum(kept) rows instead of B*S; the pipelined attention kernels read the per-sample row ranges.
+        pack = None
+        if bf and self.pack_enabled and Ln > 0 and S <= (96 if save else 128):
+            ops.pack_index(tmask, imask, ws["cu"], ws["src"])
+            Mp = int(ws["cu"][B])                     # the one host read of the step (launch shapes depend on it)
+            if Mp < M:
+                ops.rows_gather(x, ws["src"], ws["xp"], n=Mp)
+                ops.rows_gather(x_lp, ws["src"], ws["xp_lp"], n=Mp)
+                ops.rows_gather(kb.view(M, 1), ws["src"], ws["kbp"], n=Mp)
+                x, x_lp, kb = ws["xp"], ws["xp_lp"], ws["kbp"]
+                pack = (Mp, ws["cu"], ws["src"])
+        rows = pack[0] if pack else M
+        cu = pack[1] if pack else None
         nslots = len(ws["layers"])
         for l in range(Ln):
             sa, so, fi, fo = self.layer_mods[l]
             lw = ws["layers"][l % nslots]
-            x, x_lp = self._layer_fwd(lw, x, x_lp, ws["kb"], B, S, sa.query, so.dense, so.LayerNorm, fi.dense, fo.dense,
+            x, x_lp = self._layer_fwd(lw, x, x_lp, kb, B, S, sa.query, so.dense, so.LayerNorm, fi.dense, fo.dense,
                                       fo.LayerNorm, eps, 0.125, self._site(2 + 4 * l, p_a, training),
-                                      self._site(3 + 4 * l, p_h, training), self._site(4 + 4 * l, p_h, training), bf)
+                                      self._site(3 + 4 * l, p_h, training), self._site(4 + 4 * l, p_h, training), bf,
+                                      rows=rows, cu=cu)
         logits = self._head_fwd(ws, x_lp, B, S, task_id, self.pooler.dense, self.pool_act,
-                                self._site(2 + 4 * Ln, float(self.model.dropout.p), training), eps, bf)
+                                self._site(2 + 4 * Ln, float(self.model.dropout.p), training), eps, bf, pack=pack)
         if save:
             self._saved = dict(ws=ws, ids=ids, seg=seg, fa=fa, la=la, task=task_id, training=training, ticket=self._ticket,
-                               B=B, T=T, R=R, feats=feats, locs=locs)
+                               B=B, T=T, R=R, feats=feats, locs=locs, pack=pack, kb=kb)
         return logits
 
     def _layer_fwd(self, lw, x, x_lp, kb, B, S, qmod, omod, ln1, f1mod, f2mod, ln2, eps, scale, site_p, site_o, site_f, bf,
-                   row_valid=None):
+                   row_valid=None, rows=None, cu=None):
+        """rows: token rows actually present (B*S, or the packed count with cu = per-sample row ranges)"""
         d, F, H = self.d, self.F, self.H
-        ops.gemm(x_lp, self._w(qmod, 3 * d, d), lw["qkv"], bias=self._bias(qmod, 3 * d))
-        ops.attention_fwd(lw["qkv"], kb, lw["ctx"], lw["lse"], B, S, H, scale, site_p)
-        ops.gemm(lw["ctx"], self._w(omod, d, d), lw["y1"], bias=self._bias(omod, d), residual=x, dropout=site_o)
+        M = B * S if rows is None else rows
+        ops.gemm(x_lp, self._w(qmod, 3 * d, d), lw["qkv"], bias=self._bias(qmod, 3 * d), M=M)
+        ops.attention_fwd(lw["qkv"], kb, lw["ctx"], lw["lse"], B, S, H, scale, site_p, cu_rows=cu, total_rows=M if cu is not None else 0)
+        ops.gemm(lw["ctx"], self._w(omod, d, d), lw["y1"], bias=self._bias(omod, d), residual=x, dropout=site_o, M=M)
         ops.layernorm_fwd(lw["y1"], ln1.weight.data, ln1.bias.data, eps, y=lw["x1"], y_lowp=lw["x1_lp"] if bf else None,
-                          mean=lw["m1"], rstd=lw["r1"])
+                          mean=lw["m1"], rstd=lw["r1"], rows=M)
         # bf16 mode saves gelu'(u) (one shared exponential in the epilogue) so the backward epilogue is a multiply;
         # the fp32 correctness mode saves u and evaluates the exact erf / exp derivative in the backward
         ops.gemm(lw["x1_lp"], self._w(f1mod, F, d), lw["h"], bias=self._bias(f1mod, F),
-                 act=ops.ACT_GELU_GRAD if bf else ops.ACT_GELU, aux_out=lw["u"])
-        ops.gemm(lw["h"], self._w(f2mod, d, F), lw["y2"], bias=self._bias(f2mod, d), residual=lw["x1"], dropout=site_f)
+                 act=ops.ACT_GELU_GRAD if bf else ops.ACT_GELU, aux_out=lw["u"], M=M)
+        ops.gemm(lw["h"], self._w(f2mod, d, F), lw["y2"], bias=self._bias(f2mod, d), residual=lw["x1"], dropout=site_f, M=M)
         ops.layernorm_fwd(lw["y2"], ln2.weight.data, ln2.bias.data, eps, y=lw["x2"], y_lowp=lw["x2_lp"] if bf else None,
-                          mean=lw["m2"], rstd=lw["r2"], row_valid=row_valid, valid_post=row_valid is not None)
+                          mean=lw["m2"], rstd=lw["r2"], row_valid=row_valid, valid_post=row_valid is not None, rows=M)
         return lw["x2"], lw["x2_lp"]
 
-    def _head_fwd(self, ws, x_lp, B, S, task_id, pmod, pool_act, site_pool, eps_clf, bf):
+    def _first_rows(self, ws, x_lp, B, S, pack):
+        """token 0 of every sample as a [B, d] operand: a strided view, or gathered from the packed rows"""
+        if pack is None:
+            return x_lp.view(B, S * self.d)[:, :self.d]
+        ops.rows_gather(x_lp, pack[1], ws["xfirst"], n=B)
+        return ws["xfirst"]
+
+    def _head_fwd(self, ws, x_lp, B, S, task_id, pmod, pool_act, site_pool, eps_clf, bf, pack=None):
         d = self.d
         hw = ws["heads"][task_id]
         clf = self.model.clfs_dict[task_id].logit_fc
         P = self.cfg.pooler_size
-        x_first = x_lp.view(B, S * d)[:, :d]
+        x_first = self._first_rows(ws, x_lp, B, S, pack)
         ops.gemm(x_first, self._w(pmod, P, d), ws["pact"], bias=self._bias(pmod, P), act=pool_act)
         ws["pooled32"].copy_(ws["pact"])
         ops.dropout_inplace(ws["pooled32"], site_pool)            # encoders.py:L1238
@@ -615,11 +652,11 @@ class Engine:
                 self.dp.after_backward(self)
         self._saved = None
 
-    def _wgrad(self, a, b, mod0, rows, cols):
+    def _wgrad(self, a, b, mod0, rows, cols, tokens=None):
         """dW[rows, cols] += a^T b  (a: [tokens, rows], b: [tokens, cols]); SFT mask in the epilogue."""
         s = self.w_slot[id(mod0)]
         ops.gemm(a, b, self._g(s, rows, cols), a_kmajor=False, b_kmajor=False, accumulate=True,
-                 mask_bits=self._wmask(mod0))
+                 mask_bits=self._wmask(mod0), K=tokens)
 
     def _head_bwd(self, ws, sv, dl, x_lp, pmod, pool_dact, site_pool):
         d = self.d
@@ -653,40 +690,47 @@ class Engine:
         if bf:
             ops.cast_f32_to_bf16(ws["dpre"], ws["dpre_lp"])
             dpre = ws["dpre_lp"]
-        x_first = x_lp.view(B, S * d)[:, :d]
+        pack = sv.get("pack")
+        x_first = x_lp.view(B, S * d)[:, :d] if pack is None else ws["xfirst"]
         self._wgrad(dpre, x_first, pmod, P, d)
         ws["dx"].zero_()
-        ops.gemm(dpre, self._w(pmod, P, d), ws["dx"].view(B, S * d)[:, :d], b_kmajor=False)
+        if pack is None:
+            ops.gemm(dpre, self._w(pmod, P, d), ws["dx"].view(B, S * d)[:, :d], b_kmajor=False)
+        else:
+            ops.gemm(dpre, self._w(pmod, P, d), ws["dxfirst"], b_kmajor=False)
+            ops.rows_scatter(ws["dxfirst"], pack[1], ws["dx"], n=B)
 
     def _layer_bwd(self, ws, lw, x_in, x_in_lp, kb, B, S, qmod, omod, ln1, f1mod, f2mod, ln2, scale, site_p, site_o, site_f,
-                   row_valid=None):
+                   row_valid=None, rows=None, cu=None):
         """dx (ws['dx']) holds d(loss)/d(layer output) on entry and d(loss)/d(layer input) on exit."""
         d, F, H = self.d, self.F, self.H
+        M = B * S if rows is None else rows
         dx, dy, dgo = ws["dx"], ws["dy"], ws["dgo"]
         # LN2 -> residual grad dy, dropout-masked operand copy dgo, LN and FFN2-bias grads
         ops.layernorm_bwd(dx, lw["y2"], ln2.weight.data, lw["m2"], lw["r2"], dx=dy, dx_lowp=dgo,
                           dgamma=self.grad_view(ln2.weight), dbeta=self.grad_view(ln2.bias),
                           dbias=self._gvec(self.b_slot[id(f2mod)], d), dropout_in=site_f,
-                          row_valid=row_valid, valid_post=row_valid is not None)
-        self._wgrad(dgo, lw["h"], f2mod, d, F)
+                          row_valid=row_valid, valid_post=row_valid is not None, rows=M)
+        self._wgrad(dgo, lw["h"], f2mod, d, F, tokens=M)
         if ws["lp"] == torch.bfloat16:      # FFN1 bias gradient = column sums of dU, reduced inside the GEMM epilogue
             ops.gemm(dgo, self._w(f2mod, d, F), ws["du"], b_kmajor=False, act=ops.ACT_MUL_AUX, aux_in=lw["u"],
-                     colsum=self._gvec(self.b_slot[id(f1mod)], F))
+                     colsum=self._gvec(self.b_slot[id(f1mod)], F), M=M)
         else:
-            ops.gemm(dgo, self._w(f2mod, d, F), ws["du"], b_kmajor=False, act=ops.ACT_DGELU, aux_in=lw["u"])
-            ops.colsum(ws["du"], self._gvec(self.b_slot[id(f1mod)], F))
-        self._wgrad(ws["du"], lw["x1_lp"], f1mod, F, d)
-        ops.gemm(ws["du"], self._w(f1mod, F, d), dx, b_kmajor=False, residual=dy)
+            ops.gemm(dgo, self._w(f2mod, d, F), ws["du"], b_kmajor=False, act=ops.ACT_DGELU, aux_in=lw["u"], M=M)
+            ops.colsum(ws["du"], self._gvec(self.b_slot[id(f1mod)], F), M=M)
+        self._wgrad(ws["du"], lw["x1_lp"], f1mod, F, d, tokens=M)
+        ops.gemm(ws["du"], self._w(f1mod, F, d), dx, b_kmajor=False, residual=dy, M=M)
         # LN1
         ops.layernorm_bwd(dx, lw["y1"], ln1.weight.data, lw["m1"], lw["r1"], dx=dy, dx_lowp=dgo,
                           dgamma=self.grad_view(ln1.weight), dbeta=self.grad_view(ln1.bias),
-                          dbias=self._gvec(self.b_slot[id(omod)], d), dropout_in=site_o)
-        self._wgrad(dgo, lw["ctx"], omod, d, d)
-        ops.gemm(dgo, self._w(omod, d, d), ws["dctx"], b_kmajor=False)
-        ops.attention_bwd(lw["qkv"], kb, lw["ctx"], ws["dctx"], lw["lse"], ws["dqkv"], B, S, H, scale, site_p)
-        ops.colsum(ws["dqkv"], self._gvec(self.b_slot[id(qmod)], 3 * d))
-        self._wgrad(ws["dqkv"], x_in_lp, qmod, 3 * d, d)
-        ops.gemm(ws["dqkv"], self._w(qmod, 3 * d, d), dx, b_kmajor=False, residual=dy)
+                          dbias=self._gvec(self.b_slot[id(omod)], d), dropout_in=site_o, rows=M)
+        self._wgrad(dgo, lw["ctx"], omod, d, d, tokens=M)
+        ops.gemm(dgo, self._w(omod, d, d), ws["dctx"], b_kmajor=False, M=M)
+        ops.attention_bwd(lw["qkv"], kb, lw["ctx"], ws["dctx"], lw["lse"], ws["dqkv"], B, S, H, scale, site_p,
+                          cu_rows=cu, total_rows=M if cu is not None else 0)
+        ops.colsum(ws["dqkv"], self._gvec(self.b_slot[id(qmod)], 3 * d), M=M)
+        self._wgrad(ws["dqkv"], x_in_lp, qmod, 3 * d, d, tokens=M)
+        ops.gemm(ws["dqkv"], self._w(qmod, 3 * d, d), dx, b_kmajor=False, residual=dy, M=M)
 
     def _backward_uc2(self, dl, sv):
         cfg, d, Ln = self.cfg, self.d, self.L
@@ -703,19 +747,27 @@ class Engine:
         dact = ops.ACT_DRELU if self.pool_act == ops.ACT_RELU else ops.ACT_DTANH
         self._head_bwd(ws, sv, dl, x_last_lp, self.pooler.dense, dact,
                        self._site(2 + 4 * Ln, float(self.model.dropout.p), training))
+        pack = sv.get("pack")
+        rows = pack[0] if pack else None
+        cu = pack[1] if pack else None
+        kb = sv.get("kb", ws["kb"])
         for l in reversed(range(Ln)):
             sa, so, fi, fo = self.layer_mods[l]
             lw = ws["layers"][l]
             if l == 0:
-                x_in, x_in_lp = ws["x0"], ws["x0_lp"]
+                x_in, x_in_lp = (ws["xp"], ws["xp_lp"]) if pack else (ws["x0"], ws["x0_lp"])
             else:
                 x_in, x_in_lp = ws["layers"][l - 1]["x2"], ws["layers"][l - 1]["x2_lp"]
-            self._layer_bwd(ws, lw, x_in, x_in_lp, ws["kb"], B, S, sa.query, so.dense, so.LayerNorm, fi.dense, fo.dense,
+            self._layer_bwd(ws, lw, x_in, x_in_lp, kb, B, S, sa.query, so.dense, so.LayerNorm, fi.dense, fo.dense,
                             fo.LayerNorm, 0.125, self._site(2 + 4 * l, p_a, training), self._site(3 + 4 * l, p_h, training),
-                            self._site(4 + 4 * l, p_h, training))
+                            self._site(4 + 4 * l, p_h, training), rows=rows, cu=cu)
             if self.dp is not None:
                 self.dp.layer_done(self, l)
         dx = ws["dx"]
+        if pack:                                 # gradients of the kept rows back to their [B, S] positions; masked rows: 0
+            ws["dxd"].zero_()
+            ops.rows_scatter(dx, pack[2], ws["dxd"], n=pack[0])
+            dx = ws["dxd"]
         # ---- text embeddings
         ops.layernorm_bwd(dx, ws["e_txt"], E.LayerNorm.weight.data, ws["m_txt"], ws["r_txt"], dx=ws["de_txt"],
                           dgamma=self.grad_view(E.LayerNorm.weight), dbeta=self.grad_view(E.LayerNorm.bias),

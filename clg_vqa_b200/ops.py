@@ -187,7 +187,7 @@ def set_attention_backend(backend: int):
     L.check(L.load().clg_set_attention_backend(int(backend)), "clg_set_attention_backend")
 
 
-def attention_fwd(qkv, key_bias, ctx, lse, B, S, H, scale, dropout: DropSite = NO_DROP):
+def attention_fwd(qkv, key_bias, ctx, lse, B, S, H, scale, dropout: DropSite = NO_DROP, cu_rows=None, total_rows=0):
     _need_cuda(qkv, key_bias, ctx)
     p = L.AttentionFwdParams()
     p.qkv, p.ld_qkv = qkv.data_ptr(), _ld(qkv)
@@ -198,11 +198,13 @@ def attention_fwd(qkv, key_bias, ctx, lse, B, S, H, scale, dropout: DropSite = N
     p.B, p.S, p.H = int(B), int(S), int(H)
     p.scale = float(scale)
     p.dropout = dropout.c()
+    p.cu_rows, p.total_rows = _ptr(cu_rows), int(total_rows)
     L.check(L.load().clg_attention_fwd(C.byref(p), _stream()), "clg_attention_fwd")
     _count()
 
 
-def attention_bwd(qkv, key_bias, ctx, dctx, lse, dqkv, B, S, H, scale, dropout: DropSite = NO_DROP):
+def attention_bwd(qkv, key_bias, ctx, dctx, lse, dqkv, B, S, H, scale, dropout: DropSite = NO_DROP, cu_rows=None,
+                  total_rows=0):
     _need_cuda(qkv, key_bias, ctx, dctx, lse, dqkv)
     p = L.AttentionBwdParams()
     p.qkv, p.ld_qkv = qkv.data_ptr(), _ld(qkv)
@@ -215,6 +217,7 @@ def attention_bwd(qkv, key_bias, ctx, dctx, lse, dqkv, B, S, H, scale, dropout: 
     p.B, p.S, p.H = int(B), int(S), int(H)
     p.scale = float(scale)
     p.dropout = dropout.c()
+    p.cu_rows, p.total_rows = _ptr(cu_rows), int(total_rows)
     L.check(L.load().clg_attention_bwd(C.byref(p), _stream()), "clg_attention_bwd")
     _count()
 
@@ -309,6 +312,31 @@ def cast_f32_to_bf16_2d(src, dst):
     rows, cols = src.shape
     L.check(L.load().clg_cast_f32_to_bf16_2d(src.data_ptr(), _ld(src), dst.data_ptr(), _ld(dst), int(rows), int(cols), _stream()),
             "clg_cast_f32_to_bf16_2d")
+    _count()
+
+
+def pack_index(txt_mask, img_mask, cu_rows, src_rows):
+    """kept-row tables of the packed joint sequence (see clg_pack_index); cu_rows [B+1] int32, src_rows [B*(T+R)] int32"""
+    _need_cuda(txt_mask, img_mask, cu_rows, src_rows)
+    B, T = txt_mask.shape
+    L.check(L.load().clg_pack_index(txt_mask.data_ptr(), img_mask.data_ptr(), int(B), int(T), int(img_mask.shape[1]),
+                                    cu_rows.data_ptr(), src_rows.data_ptr(), _stream()), "clg_pack_index")
+    _count()
+
+
+def rows_gather(src, idx, dst, n=None):
+    """dst[i] = src[idx[i]] for i < n (2-D row-major views, same dtype / row length)"""
+    _need_cuda(src, idx, dst)
+    L.check(L.load().clg_rows_gather(src.data_ptr(), _ld(src), idx.data_ptr(), int(idx.numel() if n is None else n),
+                                     dst.data_ptr(), _ld(dst), int(src.shape[1]), _dt(src), _stream()), "clg_rows_gather")
+    _count()
+
+
+def rows_scatter(src, idx, dst, n=None):
+    """dst[idx[i]] = src[i] for i < n"""
+    _need_cuda(src, idx, dst)
+    L.check(L.load().clg_rows_scatter(src.data_ptr(), _ld(src), idx.data_ptr(), int(idx.numel() if n is None else n),
+                                      dst.data_ptr(), _ld(dst), int(src.shape[1]), _dt(src), _stream()), "clg_rows_scatter")
     _count()
 
 

@@ -199,6 +199,11 @@ typedef struct {
   int32_t B, S, H;
   float scale; int32_t _pad;
   clgDropout dropout;
+  const int32_t* cu_rows;            /* optional [B+1] (device): packed variable-length layout - sample b owns rows
+                                        [cu_rows[b], cu_rows[b+1]) of qkv / ctx (at most S of them) and key_bias is indexed by
+                                        packed row.  NULL: sample b owns rows [b*S, (b+1)*S) and key_bias is [B, S].
+                                        Only the pipelined tcgen05 kernels implement it (CLG_ERR_UNSUPPORTED otherwise). */
+  int32_t total_rows; int32_t _pad2; /* with cu_rows: cu_rows[B] (rows beyond it are never read) */
 } clgAttentionFwdParams;
 
 typedef struct {
@@ -212,6 +217,8 @@ typedef struct {
   int32_t B, S, H;
   float scale; int32_t _pad;
   clgDropout dropout;
+  const int32_t* cu_rows;            /* as in clgAttentionFwdParams */
+  int32_t total_rows; int32_t _pad2;
 } clgAttentionBwdParams;
 
 /* 0 = auto (tcgen05 kernels for bf16, FFMA kernel for fp32 / unsupported shapes), 1 = force the FFMA kernel */
@@ -330,6 +337,19 @@ int clg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, clgStream_t str
  * the [B, 1842] logit gradient needs a 16 B-aligned row pitch for TMA) */
 int clg_cast_f32_to_bf16_2d(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t rows, int32_t cols,
                             clgStream_t stream);
+/* Packing of the joint [text | regions] sequence: padded positions (mask == 0; UC2 attention_mask / image_attention_mask,
+ * encoders.py:L978-995) never influence a kept position (their key bias underflows exp() to exactly 0) and nothing reads
+ * their outputs, so the encoder layers only need the kept rows.  keep(b, s) = mask != 0 or s == 0 (token 0 feeds the pooler,
+ * encoders.py:L603-608).  cu_rows[b] = first packed row of sample b (cu_rows[B] = total), src_rows[i] = b*(T+R)+s of packed
+ * row i.  One CTA; B <= 8192. */
+int clg_pack_index(const int64_t* txt_mask, const int64_t* img_mask, int32_t B, int32_t T, int32_t R, int32_t* cu_rows,
+                   int32_t* src_rows, clgStream_t stream);
+/* dst[i, :] = src[idx[i], :] (gather) or dst[idx[i], :] = src[i, :] (scatter) for i < n; rows of `cols` elements of
+ * dtype (CLG_F32 | CLG_BF16); idx_scale multiplies the index (rows of a [B, S*d] view: the first token of every sample) */
+int clg_rows_gather(const void* src, int64_t ld_src, const int32_t* idx, int32_t n, void* dst, int64_t ld_dst, int32_t cols,
+                    int32_t dtype, clgStream_t stream);
+int clg_rows_scatter(const void* src, int64_t ld_src, const int32_t* idx, int32_t n, void* dst, int64_t ld_dst, int32_t cols,
+                     int32_t dtype, clgStream_t stream);
 /* bits[i/32] bit (i%32) = (mask[i] != 0); n multiple of 32 not required (tail bits are 0) */
 int clg_pack_mask(const float* mask, uint32_t* bits, int64_t n, clgStream_t stream);
 /* w[i] *= bit(i)  (pre-zeroing of masked weights, train_task_sft.py:L432-453) */

@@ -496,3 +496,63 @@ def test_attention_tc_matches_ffma(S, B):
         assert _rel(outs[(0, pdrop)][0], outs[(2, pdrop)][0]) < 1e-2       # same operands; exp formulated in base 2
         assert _rel(outs[(0, pdrop)][2], outs[(2, pdrop)][2]) < 8e-3     # bf16 rounding flips of dS (D_i summed in a different order)
     assert torch.isfinite(outs[(0, 0.1)][2]).all()
+
+
+@pytest.mark.parametrize("S,B", [(76, 37), (48, 9)])
+def test_attention_packed_rows_match_padded(S, B):
+    """Packed variable-length layout (clg_pack_index + cu_rows): dropping the masked positions changes nothing for the
+    kept ones - forward context and all three gradients equal the padded computation row for row."""
+    H, T = 12, 40
+    R = S - T
+    D = H * 64
+    g = torch.Generator(device="cpu").manual_seed(7)
+    tlen = torch.randint(3, T + 1, (B,), generator=g)
+    rlen = torch.randint(1, R + 1, (B,), generator=g) if R > 0 else torch.zeros(B, dtype=torch.long)
+    tm = (torch.arange(T)[None] < tlen[:, None]).long().to(DEV)
+    im = (torch.arange(R)[None] < rlen[:, None]).long().to(DEV)
+    tm[1, 0] = 0                                             # a masked first token is still kept as a query row
+    kb = torch.empty(B, S, device=DEV)
+    ops.build_key_bias(tm, im, kb)
+    qkv = _rand(B * S, 3 * D, dtype=torch.bfloat16, seed=95)
+    dctx = _rand(B * S, D, dtype=torch.bfloat16, seed=96)
+    site = DropSite(0.1, 5, 1 << 41)
+    # padded reference
+    ctx = torch.zeros(B * S, D, device=DEV, dtype=torch.bfloat16); lse = torch.zeros(B, H, S, device=DEV)
+    dqkv = torch.zeros_like(qkv)
+    ops.attention_fwd(qkv, kb, ctx, lse, B, S, H, 0.125, site)
+    ops.attention_bwd(qkv, kb, ctx, dctx, lse, dqkv, B, S, H, 0.125, site)
+    # packed
+    cu = torch.zeros(B + 1, device=DEV, dtype=torch.int32); src = torch.zeros(B * S, device=DEV, dtype=torch.int32)
+    ops.pack_index(tm, im, cu, src)
+    keep = torch.cat([tm, im], 1).bool(); keep[:, 0] = True
+    Mp = int(cu[-1])
+    assert Mp == int(keep.sum())
+    assert torch.equal(src[:Mp].long(), torch.nonzero(keep.view(-1)).flatten())
+    assert torch.equal(cu[1:].long(), keep.sum(1).cumsum(0))
+    qp = torch.full_like(qkv, float("nan")); dcp = torch.full_like(dctx, float("nan"))
+    kbp = torch.full((B * S, 1), float("nan"), device=DEV)
+    ops.rows_gather(qkv, src, qp, n=Mp); ops.rows_gather(dctx, src, dcp, n=Mp); ops.rows_gather(kb.view(-1, 1), src, kbp, n=Mp)
+    assert torch.equal(qp[:Mp], qkv[src[:Mp].long()])
+    ctxp = torch.zeros_like(ctx); lsep = torch.zeros_like(lse); dqp = torch.zeros_like(qkv)
+    ops.attention_fwd(qp, kbp, ctxp, lsep, B, S, H, 0.125, site, cu_rows=cu, total_rows=Mp)
+    ops.attention_bwd(qp, kbp, ctxp, dcp, lsep, dqp, B, S, H, 0.125, site, cu_rows=cu, total_rows=Mp)
+    sel = src[:Mp].long()
+    # the dropout stream is indexed by (sample, head, packed row, packed column): compare without dropout instead
+    ctx0 = torch.zeros_like(ctx); lse0 = torch.zeros_like(lse); dq0 = torch.zeros_like(qkv)
+    ops.attention_fwd(qkv, kb, ctx0, lse0, B, S, H, 0.125)
+    ops.attention_bwd(qkv, kb, ctx0, dctx, lse0, dq0, B, S, H, 0.125)
+    ctxp0 = torch.zeros_like(ctx); lsep0 = torch.zeros_like(lse); dqp0 = torch.zeros_like(qkv)
+    ops.attention_fwd(qp, kbp, ctxp0, lsep0, B, S, H, 0.125, cu_rows=cu, total_rows=Mp)
+    ops.attention_bwd(qp, kbp, ctxp0, dcp, lsep0, dqp0, B, S, H, 0.125, cu_rows=cu, total_rows=Mp)
+    assert _rel(ctxp0[:Mp], ctx0[sel]) < 1e-2
+    assert bool(torch.isfinite(dqp0[:Mp].float()).all())
+    # gradients of kept rows: the padded run also back-propagates through the (unused) outputs of masked query rows, so
+    # feed it a dctx that is zero there
+    dctx_m = torch.zeros_like(dctx); dctx_m[sel] = dctx[sel]
+    ops.attention_bwd(qkv, kb, ctx0, dctx_m, lse0, dq0, B, S, H, 0.125)
+    assert _rel(dqp0[:Mp], dq0[sel]) < 2e-2
+    assert bool(torch.isfinite(ctxp[:Mp].float()).all()) and bool(torch.isfinite(dqp[:Mp].float()).all())
+    # round trip of the row scatter
+    back = torch.zeros_like(qkv)
+    ops.rows_scatter(qp, src, back, n=Mp)
+    assert torch.equal(back[sel], qkv[sel]) and float(back[~keep.view(-1)].abs().max()) == 0.0
