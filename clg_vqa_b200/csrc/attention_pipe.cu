@@ -284,19 +284,11 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         tmem_wait_ld_dep32(o);
         tmem_wait_ld_dep32(o + 32);
         if (valid) {
-          if (a.cu) {             // packed layout: this row's 128 B straight to global
-            uint4* og = reinterpret_cast<uint4*>(a.out + (int64_t)(row0 + row) * a.ld_out + h * PD);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              og[j] = make_uint4(pk2(o[8 * j + 0], o[8 * j + 1]), pk2(o[8 * j + 2], o[8 * j + 3]), pk2(o[8 * j + 4], o[8 * j + 5]),
-                                 pk2(o[8 * j + 6], o[8 * j + 7]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(gO + psw_off(row, 8 * j)) =
-                  make_uint4(pk2(o[8 * j + 0], o[8 * j + 1]), pk2(o[8 * j + 2], o[8 * j + 3]), pk2(o[8 * j + 4], o[8 * j + 5]),
-                             pk2(o[8 * j + 6], o[8 * j + 7]));
-          }
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(gO + psw_off(row, 8 * j)) =
+                make_uint4(pk2(o[8 * j + 0], o[8 * j + 1]), pk2(o[8 * j + 2], o[8 * j + 3]), pk2(o[8 * j + 4], o[8 * j + 5]),
+                           pk2(o[8 * j + 6], o[8 * j + 7]));
         }
       }
       tcgen05_fence_before();
@@ -306,6 +298,15 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         fence_proxy_async();
         named_bar(1 + g, 128);
         if (tg == 0) { tma_store_2d(&tm_ctx, sO, h * PD, row0); bulk_commit(); }
+      } else {
+        // packed layout: the sample owns Sb <= S rows, a fixed-height TMA box would spill into the next sample;
+        // the group copies the staged tile out instead, 8 lanes per 128 B row (fully coalesced)
+        named_bar(1 + g, 128);
+        for (int c = tg; c < Sb * 8; c += 128) {
+          const int r = c >> 3, j = c & 7;
+          *reinterpret_cast<uint4*>(a.out + (int64_t)(row0 + r) * a.ld_out + h * PD + 8 * j) =
+              *reinterpret_cast<const uint4*>(gO + psw_off(r, 8 * j));
+        }
       }
     }
     if (tg == 0) bulk_wait_all();
@@ -576,19 +577,11 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           tmem_wait_ld_dep32(o + 32);
           if (valid) {
             const float sc = mul[which];
-            if (a.cu) {           // packed layout: row-wise stores (which-th third of the dqkv row, head h)
-              uint4* og = reinterpret_cast<uint4*>(a.out + (int64_t)(row0 + row) * a.ld_out + which * ab.Hd + h * PD);
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                og[j] = make_uint4(pk2(o[8 * j + 0] * sc, o[8 * j + 1] * sc), pk2(o[8 * j + 2] * sc, o[8 * j + 3] * sc),
-                                   pk2(o[8 * j + 4] * sc, o[8 * j + 5] * sc), pk2(o[8 * j + 6] * sc, o[8 * j + 7] * sc));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<uint4*>(stg[which] + psw_off(row, 8 * j)) =
-                    make_uint4(pk2(o[8 * j + 0] * sc, o[8 * j + 1] * sc), pk2(o[8 * j + 2] * sc, o[8 * j + 3] * sc),
-                               pk2(o[8 * j + 4] * sc, o[8 * j + 5] * sc), pk2(o[8 * j + 6] * sc, o[8 * j + 7] * sc));
-            }
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(stg[which] + psw_off(row, 8 * j)) =
+                  make_uint4(pk2(o[8 * j + 0] * sc, o[8 * j + 1] * sc), pk2(o[8 * j + 2] * sc, o[8 * j + 3] * sc),
+                             pk2(o[8 * j + 4] * sc, o[8 * j + 5] * sc), pk2(o[8 * j + 6] * sc, o[8 * j + 7] * sc));
           }
         }
       }
@@ -604,6 +597,17 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           tma_store_2d(&tm_dqkv, sdS, 2 * ab.Hd + h * PD, row0);
           bulk_commit();
         }
+      } else {
+        // packed layout (see the forward): coalesced copy-out of the three staged tiles, 8 lanes per 128 B row
+        named_bar(1 + g, 128);
+        const uint8_t* tiles[3] = {gP, gP + TN, gdS};
+#pragma unroll
+        for (int which = 0; which < 3; ++which)
+          for (int c = tg; c < Sb * 8; c += 128) {
+            const int r = c >> 3, j = c & 7;
+            *reinterpret_cast<uint4*>(a.out + (int64_t)(row0 + r) * a.ld_out + which * ab.Hd + h * PD + 8 * j) =
+                *reinterpret_cast<const uint4*>(tiles[which] + psw_off(r, 8 * j));
+          }
       }
     }
     if (tg == 0) bulk_wait_all();
