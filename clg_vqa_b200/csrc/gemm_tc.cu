@@ -549,6 +549,18 @@ int gemm_tc(const clgGemmParams& p, cudaStream_t stream) {
   else {
     const int units256 = ((num_m + 1) / 2) * ((p.N + 255) / 256);
     if (!(p.N % 256 == 0 && units256 >= sms / 2) && eff(128) > eff(256) + 0.08) bn = 128;
+    // weight-gradient shapes (few output tiles, K = tokens): 256-wide units filled up by split-K when a split count
+    // exists that keeps >= 90% of the CTA pairs busy in whole rounds (FFN wgrad: 36 units x 2 splits on 74 pairs)
+    const bool can_split = p.act == CLG_ACT_NONE && !p.bias && !p.residual && p.c_dtype == CLG_F32 && !p.dropout.p && !p.colsum &&
+                           p.split_k <= 0;
+    if (bn == 128 && can_split && p.N % 256 == 0 && p.M > BM && (p.K + BK - 1) / BK >= 32) {
+      const int clusters = sms / 2, kblocks = (p.K + BK - 1) / BK;
+      for (int sp = 2; sp <= 8 && kblocks / sp >= 8; ++sp) {
+        const int tot = units256 * sp;
+        const int rounds = (tot + clusters - 1) / clusters;
+        if ((double)tot / ((double)rounds * clusters) >= 0.9) { bn = 256; break; }
+      }
+    }
   }
   static const int force_bn = [] { const char* s = getenv("CLG_GEMM_FORCE_BN"); return s ? atoi(s) : 0; }();
   if (force_bn == 256 && p.N > 128) bn = 256;
