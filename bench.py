@@ -224,8 +224,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")                 # these levels print "NCCL version ..." on stdout: keep it to the one JSON line
         dist.init_process_group(backend="nccl", device_id=dev)
     ops.device_check(local_rank)
 
