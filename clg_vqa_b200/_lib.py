@@ -108,6 +108,7 @@ class EmbedTextBwdParams(C.Structure):
         ("dword", c_vp), ("dpos", c_vp), ("dtype_tab", c_vp),
         ("B", c_i32), ("T", c_i32), ("N", c_i32), ("pad_id", c_i32),
         ("pos_mode", c_i32), ("pos_base", c_i32), ("vocab", c_i64),
+        ("type_row0_has_total", c_i32), ("_pad", c_i32),
     ]
 
 

@@ -55,12 +55,18 @@ embed_text_bwd_kernel(const clgEmbedTextBwdParams p) {
   const float* g = p.dout + map_row(p.dout_map, tok) * p.ld_dout;
   float* dw = (p.dword && id != p.pad_id) ? p.dword + id * p.N : nullptr;   // padding_idx row gets no gradient
   float* dp = p.dpos ? p.dpos + (int64_t)pos * p.N : nullptr;
-  float* dt = (p.dtype_tab && p.seg) ? p.dtype_tab + p.seg[tok] * p.N : nullptr;
+  const int64_t sg = (p.dtype_tab && p.seg) ? p.seg[tok] : 0;
+  float* dt = (p.dtype_tab && p.seg) ? p.dtype_tab + sg * p.N : nullptr;
+  float* dt0 = nullptr;                          // row 0 correction when it was pre-loaded with the all-token total
+  if (p.type_row0_has_total && dt) {
+    if (sg == 0) dt = nullptr; else dt0 = p.dtype_tab;
+  }
   for (int c = lane; c < p.N; c += 32) {
     const float v = g[c];
     if (dw) atomicAdd(dw + c, v);
     if (dp) atomicAdd(dp + c, v);
     if (dt) atomicAdd(dt + c, v);
+    if (dt0) atomicAdd(dt0 + c, -v);
   }
 }
 

@@ -769,12 +769,15 @@ class Engine:
             ops.rows_scatter(dx, pack[2], ws["dxd"], n=pack[0])
             dx = ws["dxd"]
         # ---- text embeddings
+        ttab = E.new_token_type_embeddings.weight
+        # the LN backward also emits the column sums of de_txt over all tokens into row 0 of the token-type gradient
+        # (every GQA token has segment 0); the scatter kernel only corrects for segment-1 tokens
         ops.layernorm_bwd(dx, ws["e_txt"], E.LayerNorm.weight.data, ws["m_txt"], ws["r_txt"], dx=ws["de_txt"],
                           dgamma=self.grad_view(E.LayerNorm.weight), dbeta=self.grad_view(E.LayerNorm.bias),
-                          dy_map=rowmap(T, 0, S), dropout_out=self._site(0, p_h, training))
-        ttab = E.new_token_type_embeddings.weight
+                          dbias=self.grad_view(ttab)[0], dy_map=rowmap(T, 0, S), dropout_out=self._site(0, p_h, training))
         ops.embed_text_bwd(sv["ids"], sv["seg"], ws["de_txt"], self.grad_view(E.word_embeddings.weight),
-                           self.grad_view(E.position_embeddings.weight), self.grad_view(ttab), pad_id=cfg.pad_token_id)
+                           self.grad_view(E.position_embeddings.weight), self.grad_view(ttab), pad_id=cfg.pad_token_id,
+                           type_row0_has_total=True)
         # ---- region embeddings
         ops.layernorm_bwd(dx, ws["t2"], E.v_LayerNorm.weight.data, ws["m_v"], ws["r_v"], dx=ws["ds"],
                           dgamma=self.grad_view(E.v_LayerNorm.weight), dbeta=self.grad_view(E.v_LayerNorm.bias),

@@ -236,7 +236,8 @@ def embed_text_fwd(ids, seg, word, pos, type_tab, out, *, pad_id, out_map=None, 
     _count()
 
 
-def embed_text_bwd(ids, seg, dout, dword, dpos, dtype_tab, *, pad_id, dout_map=None, pos_mode=0, pos_base=0, N=None):
+def embed_text_bwd(ids, seg, dout, dword, dpos, dtype_tab, *, pad_id, dout_map=None, pos_mode=0, pos_base=0, N=None,
+                   type_row0_has_total=False):
     _need_cuda(ids, dout)
     p = L.EmbedTextBwdParams()
     p.ids, p.seg = ids.data_ptr(), _ptr(seg)
@@ -248,6 +249,7 @@ def embed_text_bwd(ids, seg, dout, dword, dpos, dtype_tab, *, pad_id, dout_map=N
     p.N = int(dout.shape[1] if N is None else N)
     p.pos_mode, p.pos_base = int(pos_mode), int(pos_base)
     p.vocab = int(dword.shape[0]) if dword is not None else 0
+    p.type_row0_has_total = int(bool(type_row0_has_total))
     L.check(L.load().clg_embed_text_bwd(C.byref(p), _stream()), "clg_embed_text_bwd")
     _count()
 

@@ -252,6 +252,11 @@ typedef struct {
   int32_t B, T, N, pad_id;
   int32_t pos_mode, pos_base;
   int64_t vocab;
+  int32_t type_row0_has_total;  /* 1: row 0 of dtype_tab already received the column sums over ALL tokens (emitted by the
+                                   LayerNorm backward that produced dout); segment-0 tokens then skip their type atomics
+                                   (10^4-way contention on 768 addresses) and segment-1 tokens move their share from row 0
+                                   to row 1 */
+  int32_t _pad;
 } clgEmbedTextBwdParams;
 
 int clg_embed_text_fwd(const clgEmbedTextParams* p, clgStream_t stream);
