@@ -391,6 +391,220 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 0) { __syncwarp(); tcgen05_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// backward for 128 < S <= 160 (M3P / X101: 100 regions + 40 tokens).  The single-tile kernel above puts the
+// queries on the 128 TMEM lanes; here the KEYS go on the lanes and the CTA walks two key tiles (0..127, 128..S-1):
+//   S^T_t = K_t Q^T, dP^T_t = V_t dO^T            [128 keys x NQ queries] in TMEM columns [0,160) / [160,320)
+//   P^T_t, dS^T_t (bf16) -> shared memory          one thread per key row, loop over the queries
+//   dV_t = P^T_t dO, dK_t = dS^T_t Q               complete per key tile (columns [0,64) / [64,128), reusing S^T)
+//   dQ  += dS_t K_t                                accumulated over the key tiles in columns [320,384) (queries 0..127)
+//                                                  and [384,448) (queries 128..S-1), A = (dS^T_t)^T via an MN-major descriptor
+// Shared memory: 4 KiB header (barriers, lse*log2e, D_i) | Q, dO [NQ][64] | K_t, V_t [128][64] | P^T, dS^T: 4 blocks of
+// [128][64] each (block 3 is only read as the unused upper half of the second dQ row tile).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(A_THREADS, 1)
+attn_tc_bwd_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                        const __grid_constant__ CUtensorMap tm_do, const AttnTcArgs a, const int NQ) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t TQ = (uint32_t)NQ * 128u, TB = 16384u;
+  const uint32_t sQ = base + 4096, sdO = sQ + ((TQ + 1023u) & ~1023u), sK = sdO + ((TQ + 1023u) & ~1023u), sV = sK + TB;
+  const uint32_t sPT = sV + TB, sdST = sPT + 4 * TB;
+  uint8_t* gPT = gen + (sPT - base);
+  uint8_t* gdST = gen + (sdST - base);
+  float* lse2 = reinterpret_cast<float*>(gen + 1024);
+  float* Dm = reinterpret_cast<float*>(gen + 2048);
+  volatile uint32_t* tslot = reinterpret_cast<volatile uint32_t*>(gen + 64);
+  const uint32_t bar_q = base, bar_kv = base + 8, bar_mma = base + 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x % a.H, b = blockIdx.x / a.H;
+  const int S = a.S, Hd = a.H * ADH;
+  const int n_kt = (S + 127) / 128;
+  constexpr float L2E = 1.4426950408889634f;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_do);
+    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_mma, 1);
+    fence_barrier_init(); fence_proxy_async();
+  }
+  if (warp == 0) tmem_alloc(base + 64, 512);
+  // D_i = dO_i . O_i and lse_i * log2(e) for every query row (two rows per thread when S > 128)
+  for (int i = tid; i < 192; i += A_THREADS) {
+    float di = 0.f, l2 = INFINITY;                 // rows >= S: p = 2^(-inf) = 0
+    if (i < S) {
+      const bf16* dor = a.dctx + ((int64_t)b * S + i) * a.ld_dctx + h * ADH;
+      const bf16* orow = a.ctx_in + ((int64_t)b * S + i) * a.ld_ctx + h * ADH;
+#pragma unroll
+      for (int c = 0; c < ADH; c += 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(dor + c);
+        const uint4 w = *reinterpret_cast<const uint4*>(orow + c);
+        const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&u);
+        const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 fx = __bfloat1622float2(x[t]), fy = __bfloat1622float2(y[t]);
+          di += fx.x * fy.x + fx.y * fy.y;
+        }
+      }
+      l2 = a.lse[((int64_t)b * a.H + h) * S + i] * L2E;
+    }
+    Dm[i] = di; lse2[i] = l2;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t tST = tmem, tdPT = tmem + 160, tdQA = tmem + 320, tdQB = tmem + 384, tdV = tmem, tdK = tmem + 64;
+  const uint32_t lane_off = ((uint32_t)(warp * 32) << 16);
+  const int j = warp * 32 + lane;                  // key row inside the tile == TMEM lane
+  const float scale2 = a.scale * L2E;
+  const uint64_t dhead = ((uint64_t)b * a.H + h) * (uint64_t)S;
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, 2 * TQ);
+    tma_load_2d(sQ, &tm_q, bar_q, h * ADH, b * S);
+    tma_load_2d(sdO, &tm_do, bar_q, h * ADH, b * S);
+  }
+  for (int kt = 0; kt < n_kt; ++kt) {
+    if (tid == 0) {
+      mbar_expect_tx(bar_kv, 2 * TB);
+      tma_load_2d(sK, &tm_kv, bar_kv, Hd + h * ADH, b * S + kt * 128);
+      tma_load_2d(sV, &tm_kv, bar_kv, 2 * Hd + h * ADH, b * S + kt * 128);
+      if (kt == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv, kt & 1);
+      tcgen05_fence_after();
+      const uint32_t idesc = make_idesc_mn(128, NQ, false, false);
+#pragma unroll
+      for (int k = 0; k < ADH / 16; ++k) {
+        umma_bf16(tST, umma_desc(sK + k * 32, 16, 1024), umma_desc(sQ + k * 32, 16, 1024), idesc, k > 0);
+        umma_bf16(tdPT, umma_desc(sV + k * 32, 16, 1024), umma_desc(sdO + k * 32, 16, 1024), idesc, k > 0);
+      }
+      umma_commit(bar_mma);
+    }
+    const int jg = kt * 128 + j;
+    const bool validj = jg < S;
+    const float kb2 = validj ? a.key_bias[(int64_t)b * S + jg] * L2E : -INFINITY;
+    mbar_wait(bar_mma, 0);                         // two commits per key tile: phases 0, 1
+    __syncwarp();
+    tcgen05_fence_after();
+    for (int c = 0; c < NQ; c += 16) {
+      float sv[16], dv[16];
+      tmem_ld16_nowait(tST + lane_off + c, sv);
+      tmem_ld16_nowait(tdPT + lane_off + c, dv);
+      tmem_wait_ld_dep16(sv);
+      tmem_wait_ld_dep16(dv);
+      uint32_t pp[8], dd[8];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int i = c + t;
+        float p = exp2f(fmaf(sv[t], scale2, kb2) - lse2[i]);      // 0 for masked keys and for query rows >= S
+        if (!validj) p = 0.f;
+        float dp = dv[t], pd = p;
+        if (a.drop.on) {
+          const bool keep = drop_keep(a.drop, (dhead + (uint64_t)(i < S ? i : 0)) * (uint64_t)S + (uint64_t)(validj ? jg : 0));
+          pd = keep ? p * a.drop.scale : 0.f;
+          dp = keep ? dp * a.drop.scale : 0.f;
+        }
+        const float ds = p * (dp - Dm[i]);
+        const uint32_t pb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(pd));
+        const uint32_t db = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(p > 0.f ? ds : 0.f));
+        if (t & 1) { pp[t >> 1] |= pb << 16; dd[t >> 1] |= db << 16; } else { pp[t >> 1] = pb; dd[t >> 1] = db; }
+      }
+      const int blk = c >> 6, cc = c & 63;
+      *reinterpret_cast<uint4*>(gPT + blk * TB + sw_off(j, cc)) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+      *reinterpret_cast<uint4*>(gPT + blk * TB + sw_off(j, cc + 8)) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
+      *reinterpret_cast<uint4*>(gdST + blk * TB + sw_off(j, cc)) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+      *reinterpret_cast<uint4*>(gdST + blk * TB + sw_off(j, cc + 8)) = make_uint4(dd[4], dd[5], dd[6], dd[7]);
+    }
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tcgen05_fence_after();
+      // dV_t[j,d] = sum_i P^T[j,i] dO[i,d]   A = P^T (K-major, k = i), B = dO (MN-major)
+      // dK_t[j,d] = sum_i dS^T[j,i] Q[i,d]
+      const uint32_t id_kv = make_idesc_mn(128, ADH, false, true);
+      for (int k = 0; k < NQ / 16; ++k) {
+        umma_bf16(tdV, umma_desc(sPT + (k >> 2) * TB + (k & 3) * 32, 16, 1024), umma_desc(sdO + k * 2048, 8192, 1024), id_kv, k > 0);
+        umma_bf16(tdK, umma_desc(sdST + (k >> 2) * TB + (k & 3) * 32, 16, 1024), umma_desc(sQ + k * 2048, 8192, 1024), id_kv, k > 0);
+      }
+      // dQ[i,d] += sum_j dS^T[j,i] K_t[j,d]   A = (dS^T)^T (MN-major over the [j][i] blocks, M = i), B = K_t (MN-major), k = j
+      const uint32_t id_q = make_idesc_mn(128, ADH, true, true);
+      for (int k = 0; k < 8; ++k) {
+        umma_bf16(tdQA, umma_desc(sdST + k * 2048, TB, 1024), umma_desc(sK + k * 2048, 8192, 1024), id_q, (kt > 0 || k > 0) ? 1u : 0u);
+        if (NQ > 128)
+          umma_bf16(tdQB, umma_desc(sdST + 2 * TB + k * 2048, TB, 1024), umma_desc(sK + k * 2048, 8192, 1024), id_q, (kt > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 1);
+    __syncwarp();
+    tcgen05_fence_after();
+    {
+      const uint32_t srcs[2] = {tdK, tdV};
+      const float mul[2] = {a.scale, 1.f};
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        float o[64];
+        tmem_ld32_nowait(srcs[which] + lane_off, o);
+        tmem_ld32_nowait(srcs[which] + lane_off + 32, o + 32);
+        tmem_wait_ld_dep32(o);
+        tmem_wait_ld_dep32(o + 32);
+        if (validj) {
+          uint4* og = reinterpret_cast<uint4*>(a.dqkv + ((int64_t)b * S + jg) * a.ld_dqkv + (which + 1) * Hd + h * ADH);
+          const float sc = mul[which];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * t + 0] * sc, o[8 * t + 1] * sc);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * t + 2] * sc, o[8 * t + 3] * sc);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * t + 4] * sc, o[8 * t + 5] * sc);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * t + 6] * sc, o[8 * t + 7] * sc);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            og[t] = u;
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+    __syncthreads();                               // the next key tile overwrites K_t / V_t, P^T / dS^T and S^T / dP^T
+    tcgen05_fence_after();
+  }
+  // dQ: query rows 0..127 (tile A) and 128..S-1 (tile B)
+  for (int qt = 0; qt < (NQ > 128 ? 2 : 1); ++qt) {
+    const int i = qt * 128 + j;
+    if (qt * 128 + warp * 32 < S) {
+      float o[64];
+      const uint32_t src = (qt ? tdQB : tdQA) + lane_off;
+      tmem_ld32_nowait(src, o);
+      tmem_ld32_nowait(src + 32, o + 32);
+      tmem_wait_ld_dep32(o);
+      tmem_wait_ld_dep32(o + 32);
+      if (i < S) {
+        uint4* og = reinterpret_cast<uint4*>(a.dqkv + ((int64_t)b * S + i) * a.ld_dqkv + h * ADH);
+        const float sc = a.scale;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * t + 0] * sc, o[8 * t + 1] * sc);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * t + 2] * sc, o[8 * t + 3] * sc);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * t + 4] * sc, o[8 * t + 5] * sc);
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * t + 6] * sc, o[8 * t + 7] * sc);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+          og[t] = u;
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 static int fwd_smem_bytes(int QR, int NP) {
   const int KB = (NP + 63) / 64;
   return 1024 /*align*/ + 1024 /*barriers, key bias*/ + QR * 128 + 2 * NP * 128 + KB * QR * 128 + 16384 /*read slack*/;
@@ -440,8 +654,39 @@ int attention_tc_fwd(const clgAttentionFwdParams& p, cudaStream_t stream) {
   }
 }
 
+static int attention_tc_bwd_wide(const clgAttentionBwdParams& p, cudaStream_t stream) {
+  const int NQ = (p.S + 15) / 16 * 16;
+  const int TQ = ((NQ * 128) + 1023) & ~1023;
+  const int smem = 1024 + 4096 + 2 * TQ + 2 * 16384 + 8 * 16384;
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] { err = cudaFuncSetAttribute(attn_tc_bwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); });
+  CLG_CUDA_OK(err, "cudaFuncSetAttribute(attn_tc_bwd_wide)");
+  if (smem > 232448) return CLG_ERR_UNSUPPORTED;
+  CUtensorMap tq, tkv, tdo;
+  const int64_t rows = (int64_t)p.B * p.S;
+  int st = make_tmap_bf16(&tq, p.qkv, 3LL * p.H * ADH, rows, p.ld_qkv, NQ);
+  if (st != CLG_OK) return st;
+  st = make_tmap_bf16(&tkv, p.qkv, 3LL * p.H * ADH, rows, p.ld_qkv, 128);
+  if (st != CLG_OK) return st;
+  st = make_tmap_bf16(&tdo, p.dctx, (int64_t)p.H * ADH, rows, p.ld_dctx, NQ);
+  if (st != CLG_OK) return st;
+  AttnTcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = p.B; a.S = p.S; a.H = p.H; a.NP = NQ; a.n_qt = 1;
+  a.scale = p.scale; a.key_bias = p.key_bias; a.lse = const_cast<float*>(p.lse);
+  a.ctx_in = (const bf16*)p.ctx; a.ld_ctx = p.ld_ctx;
+  a.dctx = (const bf16*)p.dctx; a.ld_dctx = p.ld_dctx;
+  a.dqkv = (bf16*)p.dqkv; a.ld_dqkv = p.ld_dqkv;
+  a.drop = make_drop(p.dropout);
+  attn_tc_bwd_wide_kernel<<<p.B * p.H, A_THREADS, smem, stream>>>(tq, tkv, tdo, a, NQ);
+  return check_launch("attn_tc_bwd_wide_kernel");
+}
+
 int attention_tc_bwd(const clgAttentionBwdParams& p, cudaStream_t stream) {
-  if (p.dtype != CLG_BF16 || p.S > 128 || p.S < 1) return CLG_ERR_UNSUPPORTED;
+  if (p.dtype != CLG_BF16 || p.S < 1) return CLG_ERR_UNSUPPORTED;
+  if (p.S > 128 && p.S <= 160) return attention_tc_bwd_wide(p, stream);
+  if (p.S > 128) return CLG_ERR_UNSUPPORTED;
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] { err = cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes(128)); });
