@@ -555,7 +555,7 @@ int gemm_tc(const clgGemmParams& p, cudaStream_t stream) {
                            p.split_k <= 0;
     if (bn == 128 && can_split && p.N % 256 == 0 && p.M > BM && (p.K + BK - 1) / BK >= 32) {
       const int clusters = sms / 2, kblocks = (p.K + BK - 1) / BK;
-      for (int sp = 2; sp <= 8 && kblocks / sp >= 8; ++sp) {
+      for (int sp = 2; sp <= 3 && kblocks / sp >= 8; ++sp) {      // more splits: measured slower than 128-wide units (QKV wgrad)
         const int tot = units256 * sp;
         const int rounds = (tot + clusters - 1) / clusters;
         if ((double)tot / ((double)rounds * clusters) >= 0.9) { bn = 256; break; }

@@ -36,6 +36,11 @@ def run(M, N, K, a_k=True, b_k=True, cdt=torch.bfloat16, res=False, bias=True, i
             e0.record(); torch.matmul(a, b.t()); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
         ts.sort(); t = ts[len(ts)//2]
         print("%-28s   cuBLAS (no epilogue)      %8.1f us  %7.1f TFLOP/s" % ("", t*1e3, 2.0*M*N*K/t/1e9))
+ONLY = os.environ.get("ONLY", "")
+_run = run
+def run(*a, **k):
+    if ONLY and ONLY not in k.get("name", ""): return
+    _run(*a, **k)
 run(8192, 8192, 8192, name="square", bias=False)
 run(19456, 2304, 768, name="QKV fwd")
 run(19456, 3072, 768, name="FFN1 (plain epi)")
@@ -51,4 +56,7 @@ run(2304, 768, 19456, a_k=False, b_k=False, cdt=torch.float32, bias=False, name=
 run(3072, 768, 19456, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="FFN1 wgrad")
 run(768, 3072, 19456, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="FFN2 wgrad")
 run(768, 768, 19456, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="out-proj wgrad")
+run(2304, 768, 15409, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="QKV wgrad K=15409")
+run(3072, 768, 15409, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="FFN1 wgrad K=15409")
+run(768, 768, 15409, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="out-proj wgrad K=15409")
 run(19456, 768, 2304, b_k=False, cdt=torch.float32, res=True, bias=False, name="QKV dgrad (+res)")
