@@ -44,6 +44,10 @@ class GemmParams(C.Structure):
     ]
 
 
+class PruneTensor(C.Structure):
+    _fields_ = [("w", c_vp), ("mask", c_vp), ("mask_out", c_vp), ("n", c_i64)]
+
+
 class LayerNormFwdParams(C.Structure):
     _fields_ = [
         ("x", c_vp), ("ldx", c_i64), ("gamma", c_vp), ("beta", c_vp),
@@ -150,6 +154,7 @@ _SIZEOF_CHECKS = {
     "clg_sizeof_gqa_loss_params": GqaLossParams,
     "clg_sizeof_adamw_params": AdamWParams,
     "clg_sizeof_tensor_meta": TensorMeta,
+    "clg_sizeof_prune_tensor": PruneTensor,
 }
 
 # every symbol include/clgvqa.h declares: name -> (restype, argtypes)
@@ -172,6 +177,8 @@ SYMBOLS = {
     "clg_adamw_step": (C.c_int, [C.POINTER(AdamWParams), c_vp]),
     "clg_cast_shadow": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "clg_cast_f32_to_bf16": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "clg_prune_hist": (C.c_int, [c_vp, C.c_int32, C.c_uint32, C.c_uint32, C.c_int32, c_vp, c_vp]),
+    "clg_prune_apply": (C.c_int, [c_vp, C.c_int32, C.c_uint32, C.c_uint64, c_vp, c_vp]),
     "clg_pack_index": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int32, C.c_int32, c_vp, c_vp, c_vp]),
     "clg_rows_gather": (C.c_int, [c_vp, c_i64, c_vp, C.c_int32, c_vp, c_i64, C.c_int32, C.c_int32, c_vp]),
     "clg_rows_scatter": (C.c_int, [c_vp, c_i64, c_vp, C.c_int32, c_vp, c_i64, C.c_int32, C.c_int32, c_vp]),

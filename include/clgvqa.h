@@ -355,6 +355,27 @@ int clg_rows_gather(const void* src, int64_t ld_src, const int32_t* idx, int32_t
                     int32_t dtype, clgStream_t stream);
 int clg_rows_scatter(const void* src, int64_t ld_src, const int32_t* idx, int32_t n, void* dst, int64_t ld_dst, int32_t cols,
                      int32_t dtype, clgStream_t stream);
+/* ------------------------------------------------------------------------------------------------
+ * Global magnitude pruning of the IMP loop (volta/train_task_prunning.py:L45-90, L728-806:
+ * prune.global_unstructured(L1Unstructured, amount) over the attention / FFN / pooler weights).
+ * tensors: device array of clgPruneTensor.  The k-th smallest |w| among the unpruned entries is found by a radix select:
+ * four clg_prune_hist passes (8-bit digit at shift 24, 16, 8, 0 over the entries whose higher key bits equal prefix;
+ * hist256 is accumulated, zero it first), the host picks the bucket between passes; clg_prune_apply then writes the new
+ * {0,1} masks: pruned where |w| < T (key order = value order for non-negative floats), and ties_to_prune of the entries
+ * equal to T (tie_counter: device scalar, zero it first).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* w;        /* weight values (the reference scores |weight_orig * weight_mask|) */
+  const float* mask;     /* current fp32 {0,1} mask or NULL (nothing pruned yet) */
+  float* mask_out;       /* new mask (may alias mask) */
+  int64_t n;
+} clgPruneTensor;
+int clg_prune_hist(const void* tensors, int32_t n_tensors, uint32_t prefix, uint32_t prefix_mask, int32_t shift,
+                   uint64_t* hist256, clgStream_t stream);
+int clg_prune_apply(const void* tensors, int32_t n_tensors, uint32_t thr_key, uint64_t ties_to_prune, uint64_t* tie_counter,
+                    clgStream_t stream);
+size_t clg_sizeof_prune_tensor(void);
+
 /* bits[i/32] bit (i%32) = (mask[i] != 0); n multiple of 32 not required (tail bits are 0) */
 int clg_pack_mask(const float* mask, uint32_t* bits, int64_t n, clgStream_t stream);
 /* w[i] *= bit(i)  (pre-zeroing of masked weights, train_task_sft.py:L432-453) */
