@@ -70,7 +70,47 @@ embed_text_bwd_kernel(const clgEmbedTextBwdParams p) {
   }
 }
 
+// Deterministic row reduction for the data-parallel word-embedding gradient: one warp per distinct token id sums
+// that id's gradient rows in the given (sorted, hence rank-independent) order and adds the result to the table row.
+// Every rank runs it on the same all-gathered list, so the replicas' gradients - and parameters - stay bit-identical.
+__global__ void __launch_bounds__(EMB_WARPS * 32)
+segment_sum_rows_kernel(const float* __restrict__ rows, int64_t ld_rows, const int32_t* __restrict__ order,
+                        const int32_t* __restrict__ seg, const int64_t* __restrict__ uniq, int n_seg, float* __restrict__ table,
+                        int N, int64_t pad_id) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * EMB_WARPS + (threadIdx.x >> 5);
+  if (w >= n_seg) return;
+  const int64_t id = uniq[w];
+  if (id == pad_id) return;
+  const int k0 = seg[w], k1 = seg[w + 1];
+  for (int c0 = 0; c0 < N; c0 += 32 * 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = k0; k < k1; ++k) {
+      const float* r = rows + (int64_t)order[k] * ld_rows;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const int c = c0 + lane + 32 * j; if (c < N) acc[j] += r[c]; }
+    }
+    float* t = table + id * N;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int c = c0 + lane + 32 * j; if (c < N) t[c] += acc[j]; }
+  }
+}
+
 }  // namespace clg
+
+extern "C" int clg_segment_sum_rows(const float* rows, int64_t ld_rows, const int32_t* order, const int32_t* seg,
+                                    const int64_t* uniq, int32_t n_seg, float* table, int32_t N, int64_t pad_id, clgStream_t stream) {
+  using namespace clg;
+  if (!rows || !order || !seg || !uniq || !table || n_seg < 0 || N <= 0) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  if (n_seg == 0) return CLG_OK;
+  segment_sum_rows_kernel<<<(unsigned)ceil_div64(n_seg, EMB_WARPS), EMB_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      rows, ld_rows, order, seg, uniq, n_seg, table, N, pad_id);
+  return check_launch("segment_sum_rows_kernel");
+}
 
 extern "C" int clg_embed_text_fwd(const clgEmbedTextParams* p, clgStream_t stream) {
   using namespace clg;

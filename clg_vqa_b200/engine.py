@@ -775,9 +775,12 @@ class Engine:
         ops.layernorm_bwd(dx, ws["e_txt"], E.LayerNorm.weight.data, ws["m_txt"], ws["r_txt"], dx=ws["de_txt"],
                           dgamma=self.grad_view(E.LayerNorm.weight), dbeta=self.grad_view(E.LayerNorm.bias),
                           dbias=self.grad_view(ttab)[0], dy_map=rowmap(T, 0, S), dropout_out=self._site(0, p_h, training))
-        ops.embed_text_bwd(sv["ids"], sv["seg"], ws["de_txt"], self.grad_view(E.word_embeddings.weight),
+        rows_mode = self.dp is not None and self.dp.rows_mode()     # data parallel: the word rows are reduced after the all-gather
+        ops.embed_text_bwd(sv["ids"], sv["seg"], ws["de_txt"], None if rows_mode else self.grad_view(E.word_embeddings.weight),
                            self.grad_view(E.position_embeddings.weight), self.grad_view(ttab), pad_id=cfg.pad_token_id,
                            type_row0_has_total=True)
+        if rows_mode:
+            self.dp.add_rows(sv["ids"], ws["de_txt"])
         # ---- region embeddings
         ops.layernorm_bwd(dx, ws["t2"], E.v_LayerNorm.weight.data, ws["m_v"], ws["r_v"], dx=ws["ds"],
                           dgamma=self.grad_view(E.v_LayerNorm.weight), dbeta=self.grad_view(E.v_LayerNorm.bias),
@@ -800,25 +803,16 @@ class Engine:
             return self.model.bert.embeddings.word_embeddings.weight
         return self.model.bert.encoder.embeddings.weight
 
-    def word_grad_rows(self):
-        """(token ids [B*T], d(loss)/d(word rows) [B*T, d], replay(ids_r, rows_r)) of the last backward:
-        another rank's contribution to the word-embedding gradient is replayed with the same
-        scatter-add kernel instead of all-reducing the dense 250002 x 768 table."""
-        sv = self._saved
-        ws = sv["ws"]
-        B, T, R = sv["B"], sv["T"], sv["R"]
+    def reduce_word_rows(self, ids: torch.Tensor, rows: torch.Tensor):
+        """word-table gradient += the (token id, gradient row) list, reduced deterministically: sorted by id (stable), one
+        warp per distinct id summing its rows in list order.  Called by parallel.GradExchange with the all-gathered list."""
         gword = self.grad_view(self.word_table_param())
-        if self.family == "uc2":
-            rows = ws["de_txt"]
-            pad = int(self.cfg.pad_token_id)
-        else:
-            rows = ws["de_joint"].view(B, T + R, self.d)[:, R:, :].reshape(B * T, self.d)
-            pad = int(getattr(self.cfg, "pad_index", 1))
-
-        def replay(ids_r, rows_r):
-            ops.embed_text_bwd(ids_r.view(B, T), None, rows_r, gword, None, None, pad_id=pad)
-
-        return sv["ids"].reshape(-1), rows, replay
+        pad = int(self.cfg.pad_token_id) if self.family == "uc2" else int(getattr(self.cfg, "pad_index", 1))
+        order = torch.argsort(ids, stable=True)
+        uniq, counts = torch.unique_consecutive(ids[order], return_counts=True)
+        seg = torch.zeros(uniq.numel() + 1, dtype=torch.int32, device=ids.device)
+        seg[1:] = counts.cumsum(0).to(torch.int32)
+        ops.segment_sum_rows(rows, order.to(torch.int32), seg, uniq.contiguous(), gword, pad)
 
     # ------------------------------------------------------------------------------------------
     # M3P (filled in by engine_m3p.py)

@@ -133,8 +133,11 @@ def backward(eng, dl, sv):
                       dropout_out=eng._site(0, p_h, training))
     gpos = eng.grad_view(enc.position_embeddings.weight)
     # text rows: word table (padding row skipped: nn.Embedding padding_idx = pad_index) + positions R..S-1
-    ops.embed_text_bwd(sv["ids"], None, de, eng.grad_view(enc.embeddings.weight), gpos, None,
+    rows_mode = eng.dp is not None and eng.dp.rows_mode()      # data parallel: word rows are reduced after the all-gather
+    ops.embed_text_bwd(sv["ids"], None, de, None if rows_mode else eng.grad_view(enc.embeddings.weight), gpos, None,
                        pad_id=int(getattr(cfg, "pad_index", 1)), dout_map=rowmap(T, R, S), pos_mode=1, pos_base=R)
+    if rows_mode:
+        eng.dp.add_rows(sv["ids"], de.view(B, S, d)[:, R:, :].reshape(B * T, d))
     # region rows: positions 0..R-1
     ops.embed_text_bwd(ws["arange_r"], None, de, None, gpos, None, pad_id=-1, dout_map=rowmap(R, 0, S), pos_mode=1,
                        pos_base=0)

@@ -254,6 +254,15 @@ def embed_text_bwd(ids, seg, dout, dword, dpos, dtype_tab, *, pad_id, dout_map=N
     _count()
 
 
+def segment_sum_rows(rows, order, seg, uniq, table, pad_id):
+    """table[uniq[s]] += sum of rows[order[seg[s]:seg[s+1]]] in list order (deterministic; see clg_segment_sum_rows)"""
+    _need_cuda(rows, order, seg, uniq, table)
+    L.check(L.load().clg_segment_sum_rows(rows.data_ptr(), _ld(rows), order.data_ptr(), seg.data_ptr(), uniq.data_ptr(),
+                                          int(uniq.numel()), table.data_ptr(), int(rows.shape[1]), int(pad_id), _stream()),
+            "clg_segment_sum_rows")
+    _count()
+
+
 def gqa_prior_loss(logits, target, dist, *, dlogits=None, row_buf, out, pred=None, topk=10, lam=10.0,
                    gscale=1.0, score_mean=True):
     _need_cuda(logits, target, row_buf, out)

@@ -10,8 +10,9 @@ Here
   * the dense part is all-reduced IN PLACE in per-layer buckets that are launched as soon as the layer's
     backward has been enqueued, so NCCL overlaps the rest of the backward;
   * the 192 M-parameter word-embedding gradient is row-sparse (<= B*40 rows): ranks all-gather the
-    per-token gradient rows + token ids (31 MB per rank at B=256) and replay each other's scatter-add
-    instead of all-reducing 768 MB;
+    per-token gradient rows + token ids (31 MB per rank at B=256) instead of all-reducing 768 MB, and every rank
+    reduces the SAME gathered list in the SAME order (sorted by token id, one warp per id: `reduce_rows`), so the
+    replicas' gradients, clip coefficients and parameters stay bit-identical, as they do under apex's all-reduce;
   * the 1/world average is folded into the optimiser kernel's gradient read (AdamW.grad_scale);
   * with gradient accumulation, `no_sync()` skips the exchange on all but the last micro-step.
 The class only needs `torch.distributed` collectives, so its logic is exercised with gloo on CPU.
@@ -32,6 +33,8 @@ class GradExchange:
         self.pending = []            # async work handles of the current backward
         self.enabled = True
         self.done_ranges: List[Tuple[int, int]] = []
+        self.row_ids: List[torch.Tensor] = []      # word-gradient rows of the micro-steps since the last exchange
+        self.row_vals: List[torch.Tensor] = []
 
     # -- generic pieces (device-agnostic; tested with gloo) ---------------------------------------
     def reduce_range(self, flat: torch.Tensor, start: int, end: int):
@@ -59,6 +62,31 @@ class GradExchange:
         for r in range(self.world):
             if r != me:
                 replay(all_ids[r], all_rows[r])
+
+    def add_rows(self, ids: torch.Tensor, rows: torch.Tensor):
+        """word-table gradient rows of one backward (kept until the next exchange; micro-steps inside no_sync() pile up)"""
+        self.row_ids.append(ids.reshape(-1).clone())
+        self.row_vals.append(rows.reshape(ids.numel(), -1).clone())
+
+    def exchange_rows_deterministic(self, reduce_rows: Callable[[torch.Tensor, torch.Tensor], None]):
+        """all-gather every stashed (id, row) and hand the rank-ordered concatenation to reduce_rows(ids, rows), which must
+        reduce it in an order that does not depend on the calling rank"""
+        if not self.row_ids:
+            return
+        ids = torch.cat(self.row_ids) if len(self.row_ids) > 1 else self.row_ids[0]
+        rows = torch.cat(self.row_vals) if len(self.row_vals) > 1 else self.row_vals[0]
+        self.row_ids, self.row_vals = [], []
+        if self.world > 1:
+            all_ids = torch.empty(self.world * ids.numel(), dtype=ids.dtype, device=ids.device)
+            all_rows = torch.empty((self.world * rows.shape[0], rows.shape[1]), dtype=rows.dtype, device=rows.device)
+            dist.all_gather_into_tensor(all_ids, ids, group=self.group)
+            dist.all_gather_into_tensor(all_rows.view(-1), rows.reshape(-1), group=self.group)
+            ids, rows = all_ids, all_rows
+        reduce_rows(ids, rows)
+
+    def rows_mode(self) -> bool:
+        """True: the engine must not scatter its word-table gradient itself but hand the rows to add_rows()"""
+        return self.world > 1
 
     def finish(self):
         for w in self.pending:
@@ -113,8 +141,7 @@ class GradExchange:
             cur = max(cur, b)
         if cur < engine.total:
             self.reduce_range(engine.g_flat, cur, engine.total)
-        ids, rows, replay = engine.word_grad_rows()
-        self.exchange_rows(ids, rows, replay)
+        self.exchange_rows_deterministic(engine.reduce_word_rows)
         self.finish()
 
 

@@ -56,6 +56,30 @@ def _worker(rank, world, port, out):
             ex.reduce_range(keep, 0, 4096)
             ex.finish()
         ok = ok and torch.equal(keep, dense)
+        # deterministic row exchange: rows of two micro-steps (the first inside no_sync) are stashed, all-gathered once and
+        # reduced from the same rank-ordered list on every rank -> bit-identical tables
+        ids2 = torch.randint(0, V, (NTOK,)); rows2 = torch.randn(NTOK, D)
+        with ex.no_sync():
+            ex.add_rows(ids, rows)
+        ex.add_rows(ids2, rows2)
+        t2 = torch.zeros(V, D)
+        seen = {}
+
+        def reduce_rows(i, r):
+            seen["n"] = i.numel()
+            order = torch.argsort(i, stable=True)
+            t2.index_add_(0, i[order], r[order])
+        ex.exchange_rows_deterministic(reduce_rows)
+        ok = ok and seen.get("n") == 2 * NTOK * world and ex.row_ids == []
+        all_i2 = [torch.zeros_like(ids2) for _ in range(world)]; all_r2 = [torch.zeros_like(rows2) for _ in range(world)]
+        dist.all_gather(all_i2, ids2); dist.all_gather(all_r2, rows2)
+        ref2 = ref_table.clone()
+        for i, r in zip(all_i2, all_r2):
+            ref2.index_add_(0, i, r)
+        ok = ok and torch.allclose(t2, ref2, atol=1e-5)
+        all_t2 = [torch.zeros_like(t2) for _ in range(world)]
+        dist.all_gather(all_t2, t2)
+        ok = ok and all(torch.equal(all_t2[0], t) for t in all_t2)       # replicas bit-identical
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
