@@ -70,45 +70,36 @@ embed_text_bwd_kernel(const clgEmbedTextBwdParams p) {
   }
 }
 
-// Deterministic row reduction for the data-parallel word-embedding gradient: one warp per distinct token id sums
-// that id's gradient rows in the given (sorted, hence rank-independent) order and adds the result to the table row.
-// Every rank runs it on the same all-gathered list, so the replicas' gradients - and parameters - stay bit-identical.
-__global__ void __launch_bounds__(EMB_WARPS * 32)
-segment_sum_rows_kernel(const float* __restrict__ rows, int64_t ld_rows, const int32_t* __restrict__ order,
-                        const int32_t* __restrict__ seg, const int64_t* __restrict__ uniq, int n_seg, float* __restrict__ table,
-                        int N, int64_t pad_id) {
-  const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * EMB_WARPS + (threadIdx.x >> 5);
-  if (w >= n_seg) return;
-  const int64_t id = uniq[w];
-  if (id == pad_id) return;
-  const int k0 = seg[w], k1 = seg[w + 1];
-  for (int c0 = 0; c0 < N; c0 += 32 * 8) {
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int k = k0; k < k1; ++k) {
-      const float* r = rows + (int64_t)order[k] * ld_rows;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const int c = c0 + lane + 32 * j; if (c < N) acc[j] += r[c]; }
-    }
-    float* t = table + id * N;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { const int c = c0 + lane + 32 * j; if (c < N) t[c] += acc[j]; }
+// Deterministic row reduction for the data-parallel word-embedding gradient.  Input: the all-gathered (token id,
+// gradient row) list sorted by id (stable).  One CTA per list position; the CTA at the head of a run of equal ids sums
+// that run's rows in list order (the warps split the columns) and adds the result to the table row.  Every rank runs it
+// on the same list, so the replicas' gradients - and parameters - stay bit-identical.  No host-side unique / sync.
+__global__ void __launch_bounds__(256)
+segment_sum_rows_kernel(const float* __restrict__ rows, int64_t ld_rows, const int64_t* __restrict__ order,
+                        const int64_t* __restrict__ sorted_ids, int n, float* __restrict__ table, int N, int64_t pad_id) {
+  const int k0 = blockIdx.x;
+  const int64_t id = sorted_ids[k0];
+  if (id == pad_id || (k0 > 0 && sorted_ids[k0 - 1] == id)) return;      // not the head of a run
+  int k1 = k0 + 1;
+  while (k1 < n && sorted_ids[k1] == id) ++k1;
+  float* t = table + id * N;
+  for (int c = threadIdx.x; c < N; c += 256) {
+    float acc = 0.f;
+    for (int k = k0; k < k1; ++k) acc += rows[order[k] * ld_rows + c];
+    t[c] += acc;
   }
 }
 
 }  // namespace clg
 
-extern "C" int clg_segment_sum_rows(const float* rows, int64_t ld_rows, const int32_t* order, const int32_t* seg,
-                                    const int64_t* uniq, int32_t n_seg, float* table, int32_t N, int64_t pad_id, clgStream_t stream) {
+extern "C" int clg_segment_sum_rows(const float* rows, int64_t ld_rows, const int64_t* order, const int64_t* sorted_ids, int32_t n,
+                                    float* table, int32_t N, int64_t pad_id, clgStream_t stream) {
   using namespace clg;
-  if (!rows || !order || !seg || !uniq || !table || n_seg < 0 || N <= 0) return CLG_ERR_ARG;
+  if (!rows || !order || !sorted_ids || !table || n < 0 || N <= 0) return CLG_ERR_ARG;
   int st = require_sm100();
   if (st != CLG_OK) return st;
-  if (n_seg == 0) return CLG_OK;
-  segment_sum_rows_kernel<<<(unsigned)ceil_div64(n_seg, EMB_WARPS), EMB_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      rows, ld_rows, order, seg, uniq, n_seg, table, N, pad_id);
+  if (n == 0) return CLG_OK;
+  segment_sum_rows_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, ld_rows, order, sorted_ids, n, table, N, pad_id);
   return check_launch("segment_sum_rows_kernel");
 }
 

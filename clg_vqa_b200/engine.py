@@ -808,11 +808,8 @@ class Engine:
         warp per distinct id summing its rows in list order.  Called by parallel.GradExchange with the all-gathered list."""
         gword = self.grad_view(self.word_table_param())
         pad = int(self.cfg.pad_token_id) if self.family == "uc2" else int(getattr(self.cfg, "pad_index", 1))
-        order = torch.argsort(ids, stable=True)
-        uniq, counts = torch.unique_consecutive(ids[order], return_counts=True)
-        seg = torch.zeros(uniq.numel() + 1, dtype=torch.int32, device=ids.device)
-        seg[1:] = counts.cumsum(0).to(torch.int32)
-        ops.segment_sum_rows(rows, order.to(torch.int32), seg, uniq.contiguous(), gword, pad)
+        sorted_ids, order = torch.sort(ids, stable=True)           # index bookkeeping only; no host sync
+        ops.segment_sum_rows(rows, order, sorted_ids, gword, pad)
 
     # ------------------------------------------------------------------------------------------
     # M3P (filled in by engine_m3p.py)

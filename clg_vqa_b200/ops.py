@@ -254,11 +254,11 @@ def embed_text_bwd(ids, seg, dout, dword, dpos, dtype_tab, *, pad_id, dout_map=N
     _count()
 
 
-def segment_sum_rows(rows, order, seg, uniq, table, pad_id):
-    """table[uniq[s]] += sum of rows[order[seg[s]:seg[s+1]]] in list order (deterministic; see clg_segment_sum_rows)"""
-    _need_cuda(rows, order, seg, uniq, table)
-    L.check(L.load().clg_segment_sum_rows(rows.data_ptr(), _ld(rows), order.data_ptr(), seg.data_ptr(), uniq.data_ptr(),
-                                          int(uniq.numel()), table.data_ptr(), int(rows.shape[1]), int(pad_id), _stream()),
+def segment_sum_rows(rows, order, sorted_ids, table, pad_id):
+    """table[id] += sum of rows[order[k]] over each run of equal sorted_ids, in list order (see clg_segment_sum_rows)"""
+    _need_cuda(rows, order, sorted_ids, table)
+    L.check(L.load().clg_segment_sum_rows(rows.data_ptr(), _ld(rows), order.data_ptr(), sorted_ids.data_ptr(),
+                                          int(sorted_ids.numel()), table.data_ptr(), int(rows.shape[1]), int(pad_id), _stream()),
             "clg_segment_sum_rows")
     _count()
 

@@ -65,8 +65,11 @@ class GradExchange:
 
     def add_rows(self, ids: torch.Tensor, rows: torch.Tensor):
         """word-table gradient rows of one backward (kept until the next exchange; micro-steps inside no_sync() pile up)"""
-        self.row_ids.append(ids.reshape(-1).clone())
-        self.row_vals.append(rows.reshape(ids.numel(), -1).clone())
+        ids, rows = ids.reshape(-1), rows.reshape(ids.numel(), -1)
+        if not self.enabled:                       # accumulation micro-step: the engine reuses these buffers before the exchange
+            ids, rows = ids.clone(), rows.clone()
+        self.row_ids.append(ids)
+        self.row_vals.append(rows)
 
     def exchange_rows_deterministic(self, reduce_rows: Callable[[torch.Tensor, torch.Tensor], None]):
         """all-gather every stashed (id, row) and hand the rank-ordered concatenation to reduce_rows(ids, rows), which must

@@ -259,12 +259,13 @@ typedef struct {
   int32_t _pad;
 } clgEmbedTextBwdParams;
 
-/* table[uniq[s], :] += sum_{k in [seg[s], seg[s+1])} rows[order[k], :] (skipping uniq[s] == pad_id), summed in list order by
- * one warp per segment - a deterministic replacement of the atomic scatter for the data-parallel word-embedding gradient
- * (apex all-reduces the dense 250002 x 768 table, distributed.py:L491-510; here every rank reduces the same all-gathered
- * (token id, gradient row) list in the same order, so the replicas stay bit-identical). */
-int clg_segment_sum_rows(const float* rows, int64_t ld_rows, const int32_t* order, const int32_t* seg, const int64_t* uniq,
-                         int32_t n_seg, float* table, int32_t N, int64_t pad_id, clgStream_t stream);
+/* sorted_ids[n]: token ids sorted ascending (stable), order[n]: the row index of each sorted entry.  For every run of
+ * equal ids (!= pad_id): table[id, :] += sum of rows[order[k], :] over the run, in list order, by one CTA - a deterministic
+ * replacement of the atomic scatter for the data-parallel word-embedding gradient (apex all-reduces the dense 250002 x 768
+ * table, distributed.py:L491-510; here every rank reduces the same all-gathered (token id, gradient row) list in the same
+ * order, so the replicas stay bit-identical). */
+int clg_segment_sum_rows(const float* rows, int64_t ld_rows, const int64_t* order, const int64_t* sorted_ids, int32_t n,
+                         float* table, int32_t N, int64_t pad_id, clgStream_t stream);
 int clg_embed_text_fwd(const clgEmbedTextParams* p, clgStream_t stream);
 int clg_embed_text_bwd(const clgEmbedTextBwdParams* p, clgStream_t stream);
 size_t clg_sizeof_embed_text_params(void);
