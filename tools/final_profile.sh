@@ -10,7 +10,7 @@ python tools/profile_step.py > $out/prof_plain.log 2>&1 || { echo "profile_step 
 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
     --log-file $out/${tag}_launches_step_b256.csv python tools/profile_step.py > $out/ncu_list.log 2>&1
 tail -1 $out/ncu_list.log
-for spec in "wgrad:gemm_tc:45" "ffn1:gemm_tc:20" "attn_bwd:attn_pipe_bwd:3" "attn_fwd:attn_pipe_fwd:3" "adamw:adamw_kernel:0"; do
+for spec in "gemm_qkv_plain:gemm_tc:45" "gemm_resid:gemm_tc:20" "attn_bwd:attn_pipe_bwd:3" "attn_fwd:attn_pipe_fwd:3" "adamw:adamw_kernel:0"; do
   name=${spec%%:*}; rest=${spec#*:}; kern=${rest%%:*}; skip=${rest#*:}
   ncu --profile-from-start off --set full --clock-control none -k regex:$kern -s $skip -c 1 -o /tmp/full_$name -f python tools/profile_step.py > $out/ncu_full_$name.log 2>&1
   ncu -i /tmp/full_$name.ncu-rep --page details > $out/${tag}_ncu_full_$name.txt 2>/dev/null
