@@ -170,7 +170,7 @@ SYMBOLS = {
     "clg_set_attention_backend": (C.c_int, [C.c_int]),
     "clg_attention_fwd": (C.c_int, [C.POINTER(AttentionFwdParams), c_vp]),
     "clg_attention_bwd": (C.c_int, [C.POINTER(AttentionBwdParams), c_vp]),
-    "clg_segment_sum_rows": (C.c_int, [c_vp, c_i64, c_vp, c_vp, C.c_int32, c_vp, C.c_int32, c_i64, c_vp]),
+    "clg_segment_sum_rows": (C.c_int, [c_vp, c_i64, c_vp, c_vp, C.c_int32, c_vp, C.c_int32, c_i64, C.c_int32, c_vp, c_vp]),
     "clg_embed_text_fwd": (C.c_int, [C.POINTER(EmbedTextParams), c_vp]),
     "clg_embed_text_bwd": (C.c_int, [C.POINTER(EmbedTextBwdParams), c_vp]),
     "clg_gqa_prior_loss": (C.c_int, [C.POINTER(GqaLossParams), c_vp]),

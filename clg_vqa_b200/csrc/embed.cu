@@ -74,32 +74,56 @@ embed_text_bwd_kernel(const clgEmbedTextBwdParams p) {
 // gradient row) list sorted by id (stable).  One CTA per list position; the CTA at the head of a run of equal ids sums
 // that run's rows in list order (the warps split the columns) and adds the result to the table row.  Every rank runs it
 // on the same list, so the replicas' gradients - and parameters - stay bit-identical.  No host-side unique / sync.
+// mode 0: table[id, :] += run sum.   mode 1 (local pre-reduction before the all-gather): the run sum replaces the run's
+// FIRST row in `rows` and the other members get ids_out = pad_id, so that after the all-gather an id occurs at most once
+// per rank and no run is longer than the world size.
+// The 8 warps of the CTA split a run into 8 contiguous pieces (fixed by the run length only), each warp sums its piece in
+// list order over all columns, and the pieces are combined in warp order: deterministic, and 8x shorter chains for the
+// long runs (<s>, </s> occur once per sample).
 __global__ void __launch_bounds__(256)
-segment_sum_rows_kernel(const float* __restrict__ rows, int64_t ld_rows, const int64_t* __restrict__ order,
-                        const int64_t* __restrict__ sorted_ids, int n, float* __restrict__ table, int N, int64_t pad_id) {
+segment_sum_rows_kernel(float* __restrict__ rows, int64_t ld_rows, const int64_t* __restrict__ order,
+                        const int64_t* __restrict__ sorted_ids, int n, float* __restrict__ table, int N, int64_t pad_id, int mode,
+                        int64_t* __restrict__ ids_out) {
+  extern __shared__ float part[];                 // [8][N]
   const int k0 = blockIdx.x;
   const int64_t id = sorted_ids[k0];
   if (id == pad_id || (k0 > 0 && sorted_ids[k0 - 1] == id)) return;      // not the head of a run
   int k1 = k0 + 1;
   while (k1 < n && sorted_ids[k1] == id) ++k1;
-  float* t = table + id * N;
-  for (int c = threadIdx.x; c < N; c += 256) {
+  const int len = k1 - k0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (len == 1 && mode == 1) return;              // a single row is already its own sum
+  const int per = (len + 7) / 8;
+  const int a = k0 + warp * per, b = min(k1, a + per);
+  for (int c = lane; c < N; c += 32) {
     float acc = 0.f;
-    for (int k = k0; k < k1; ++k) acc += rows[order[k] * ld_rows + c];
-    t[c] += acc;
+    for (int k = a; k < b; ++k) acc += rows[order[k] * ld_rows + c];
+    part[warp * N + c] = acc;
   }
+  __syncthreads();
+  float* dst = mode == 0 ? table + id * N : rows + order[k0] * ld_rows;
+  for (int c = threadIdx.x; c < N; c += 256) {
+    float acc = part[c];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) acc += part[w * N + c];
+    if (mode == 0) dst[c] += acc; else dst[c] = acc;
+  }
+  if (mode == 1)
+    for (int k = k0 + 1 + threadIdx.x; k < k1; k += 256) ids_out[order[k]] = pad_id;
 }
 
 }  // namespace clg
 
-extern "C" int clg_segment_sum_rows(const float* rows, int64_t ld_rows, const int64_t* order, const int64_t* sorted_ids, int32_t n,
-                                    float* table, int32_t N, int64_t pad_id, clgStream_t stream) {
+extern "C" int clg_segment_sum_rows(float* rows, int64_t ld_rows, const int64_t* order, const int64_t* sorted_ids, int32_t n,
+                                    float* table, int32_t N, int64_t pad_id, int32_t mode, int64_t* ids_out, clgStream_t stream) {
   using namespace clg;
-  if (!rows || !order || !sorted_ids || !table || n < 0 || N <= 0) return CLG_ERR_ARG;
+  if (!rows || !order || !sorted_ids || n < 0 || N <= 0 || N > 4096) return CLG_ERR_ARG;
+  if ((mode == 0 && !table) || (mode == 1 && !ids_out) || (mode != 0 && mode != 1)) return CLG_ERR_ARG;
   int st = require_sm100();
   if (st != CLG_OK) return st;
   if (n == 0) return CLG_OK;
-  segment_sum_rows_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, ld_rows, order, sorted_ids, n, table, N, pad_id);
+  segment_sum_rows_kernel<<<n, 256, 8 * N * sizeof(float), static_cast<cudaStream_t>(stream)>>>(rows, ld_rows, order, sorted_ids, n, table,
+                                                                                              N, pad_id, mode, ids_out);
   return check_launch("segment_sum_rows_kernel");
 }
 

@@ -254,12 +254,13 @@ def embed_text_bwd(ids, seg, dout, dword, dpos, dtype_tab, *, pad_id, dout_map=N
     _count()
 
 
-def segment_sum_rows(rows, order, sorted_ids, table, pad_id):
-    """table[id] += sum of rows[order[k]] over each run of equal sorted_ids, in list order (see clg_segment_sum_rows)"""
-    _need_cuda(rows, order, sorted_ids, table)
+def segment_sum_rows(rows, order, sorted_ids, table, pad_id, ids_out=None):
+    """runs of equal sorted_ids summed in list order (see clg_segment_sum_rows): into table (ids_out None) or, as a local
+    pre-reduction, into the run's first row with the other members' ids_out set to pad_id"""
+    _need_cuda(rows, order, sorted_ids)
     L.check(L.load().clg_segment_sum_rows(rows.data_ptr(), _ld(rows), order.data_ptr(), sorted_ids.data_ptr(),
-                                          int(sorted_ids.numel()), table.data_ptr(), int(rows.shape[1]), int(pad_id), _stream()),
-            "clg_segment_sum_rows")
+                                          int(sorted_ids.numel()), _ptr(table), int(rows.shape[1]), int(pad_id),
+                                          0 if ids_out is None else 1, _ptr(ids_out), _stream()), "clg_segment_sum_rows")
     _count()
 
 

@@ -71,7 +71,8 @@ class GradExchange:
         self.row_ids.append(ids)
         self.row_vals.append(rows)
 
-    def exchange_rows_deterministic(self, reduce_rows: Callable[[torch.Tensor, torch.Tensor], None]):
+    def exchange_rows_deterministic(self, reduce_rows: Callable[[torch.Tensor, torch.Tensor], None],
+                                    prereduce: Optional[Callable[[torch.Tensor, torch.Tensor], torch.Tensor]] = None):
         """all-gather every stashed (id, row) and hand the rank-ordered concatenation to reduce_rows(ids, rows), which must
         reduce it in an order that does not depend on the calling rank"""
         if not self.row_ids:
@@ -79,6 +80,10 @@ class GradExchange:
         ids = torch.cat(self.row_ids) if len(self.row_ids) > 1 else self.row_ids[0]
         rows = torch.cat(self.row_vals) if len(self.row_vals) > 1 else self.row_vals[0]
         self.row_ids, self.row_vals = [], []
+        if prereduce is not None and self.world > 1:
+            if not rows.is_contiguous():
+                rows = rows.contiguous()
+            ids = prereduce(ids, rows)            # in place on rows; duplicates renamed to the padding id
         if self.world > 1:
             all_ids = torch.empty(self.world * ids.numel(), dtype=ids.dtype, device=ids.device)
             all_rows = torch.empty((self.world * rows.shape[0], rows.shape[1]), dtype=rows.dtype, device=rows.device)
@@ -144,7 +149,7 @@ class GradExchange:
             cur = max(cur, b)
         if cur < engine.total:
             self.reduce_range(engine.g_flat, cur, engine.total)
-        self.exchange_rows_deterministic(engine.reduce_word_rows)
+        self.exchange_rows_deterministic(engine.reduce_word_rows, engine.prereduce_word_rows)
         self.finish()
 
 

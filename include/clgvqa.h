@@ -260,12 +260,14 @@ typedef struct {
 } clgEmbedTextBwdParams;
 
 /* sorted_ids[n]: token ids sorted ascending (stable), order[n]: the row index of each sorted entry.  For every run of
- * equal ids (!= pad_id): table[id, :] += sum of rows[order[k], :] over the run, in list order, by one CTA - a deterministic
- * replacement of the atomic scatter for the data-parallel word-embedding gradient (apex all-reduces the dense 250002 x 768
+ * equal ids (!= pad_id) the rows[order[k], :] of the run are summed in list order by one CTA (deterministic: 8 contiguous
+ * pieces combined in order).  mode 0: table[id, :] += sum.  mode 1: the sum replaces the run's first row and
+ * ids_out[order[k]] = pad_id for the other members (local pre-reduction: afterwards an id occurs once).
+ * Replaces the atomic scatter for the data-parallel word-embedding gradient (apex all-reduces the dense 250002 x 768
  * table, distributed.py:L491-510; here every rank reduces the same all-gathered (token id, gradient row) list in the same
  * order, so the replicas stay bit-identical). */
-int clg_segment_sum_rows(const float* rows, int64_t ld_rows, const int64_t* order, const int64_t* sorted_ids, int32_t n,
-                         float* table, int32_t N, int64_t pad_id, clgStream_t stream);
+int clg_segment_sum_rows(float* rows, int64_t ld_rows, const int64_t* order, const int64_t* sorted_ids, int32_t n,
+                         float* table, int32_t N, int64_t pad_id, int32_t mode, int64_t* ids_out, clgStream_t stream);
 int clg_embed_text_fwd(const clgEmbedTextParams* p, clgStream_t stream);
 int clg_embed_text_bwd(const clgEmbedTextBwdParams* p, clgStream_t stream);
 size_t clg_sizeof_embed_text_params(void);

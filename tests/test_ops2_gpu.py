@@ -132,3 +132,33 @@ def test_adamw_cold_blocks_bit_identical_to_dense():
     assert int(hot[k // 256:].sum()) == 0
     assert 0.05 < float(touched.float().mean()) < 0.5           # the test exercises both paths
     assert torch.equal(state["hot"][0][start2:start2 + k2], torch.ones(k2, device=DEV))
+
+
+def test_segment_sum_rows_deterministic_reduction():
+    """data-parallel word-gradient reduction: local pre-reduction (duplicates summed into the first row, other copies renamed
+    to the padding id) followed by the table reduction equals index_add; two runs give bit-identical tables"""
+    n, d, V, pad = 5000, 768, 300, 1
+    g = torch.Generator(device="cpu").manual_seed(5)
+    ids = torch.randint(0, V, (n,), generator=g)
+    ids[::7] = 0; ids[3::11] = 2                                 # long runs (<s>, </s>)
+    rows = torch.randn(n, d, generator=g)
+    ref = torch.zeros(V, d, dtype=torch.float64).index_add_(0, ids, rows.double())
+    ref[pad] = 0
+    outs = []
+    for _ in range(2):
+        ids_d, rows_d = ids.to(DEV), rows.to(DEV).clone()
+        ids_out = ids_d.clone()
+        s_ids, order = torch.sort(ids_d, stable=True)
+        ops.segment_sum_rows(rows_d, order, s_ids, None, pad, ids_out=ids_out)
+        assert int((ids_out != pad).sum()) == len(set(ids.tolist()) - {pad})          # one surviving row per distinct id
+        s2, o2 = torch.sort(ids_out, stable=True)
+        table = torch.zeros(V, d, device=DEV)
+        ops.segment_sum_rows(rows_d, o2, s2, table, pad)
+        outs.append(table)
+        assert float((table.double().cpu() - ref).abs().max()) < 1e-3
+    assert torch.equal(outs[0], outs[1])
+    # direct (no pre-reduction) gives the same values up to summation order
+    table2 = torch.zeros(V, d, device=DEV)
+    s_ids, order = torch.sort(ids.to(DEV), stable=True)
+    ops.segment_sum_rows(rows.to(DEV), order, s_ids, table2, pad)
+    assert float((table2.double().cpu() - ref).abs().max()) < 1e-3
