@@ -165,6 +165,7 @@ SYMBOLS = {
     "clg_device_check": (C.c_int, [C.c_int]),
     "clg_num_sms": (C.c_int, [C.c_int]),
     "clg_gemm": (C.c_int, [C.POINTER(GemmParams), c_vp]),
+    "clg_set_gemm_sm_limit": (C.c_int, [C.c_int]),
     "clg_layernorm_fwd": (C.c_int, [C.POINTER(LayerNormFwdParams), c_vp]),
     "clg_layernorm_bwd": (C.c_int, [C.POINTER(LayerNormBwdParams), c_vp]),
     "clg_set_attention_backend": (C.c_int, [C.c_int]),

@@ -372,6 +372,17 @@ int make_tmap_epi(CUtensorMap* m, const void* ptr, int dtype, int64_t inner, int
   return CLG_OK;
 }
 
+// SMs the persistent GEMM grids occupy.  Under data parallelism NCCL's all-reduce kernels run concurrently with the
+// backward GEMMs: with one persistent CTA per SM and a static tile schedule, a CTA whose SM is held by a NCCL CTA starts
+// late and the whole GEMM waits for it.  clg_set_gemm_sm_limit(n) (parallel.attach) leaves sms - n SMs to NCCL.
+static int g_gemm_sm_limit = 0;
+static int gemm_sms() {
+  static const int env = [] { const char* s = getenv("CLG_GEMM_SMS"); return s ? atoi(s) : 0; }();
+  const int lim = env > 0 ? env : g_gemm_sm_limit;
+  const int sms = num_sms();
+  return (lim > 0 && lim < sms) ? (lim & ~1) : sms;
+}
+
 static bool env_flag(const char* name, bool dflt) {
   const char* s = getenv(name);
   if (!s || !s[0]) return dflt;
@@ -421,7 +432,7 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
   t.num_m = (p.M + BM - 1) / BM;
   t.num_n = (p.N + BN - 1) / BN;
   t.kblocks = (p.K + BK - 1) / BK;
-  const int sms = num_sms();
+  const int sms = gemm_sms();
   int splits = p.split_k;
   const bool can_split = (EPI == EPI_GENERIC && p.act == CLG_ACT_NONE && p.bias == nullptr && p.residual == nullptr &&
                           p.c_dtype == CLG_F32 && !p.dropout.p);
@@ -533,7 +544,7 @@ int gemm_tc(const clgGemmParams& p, cudaStream_t stream) {
   const EpiArgs e = make_epi(p);
   // Tile choice: BN = 256 when the tile count still fills the machine in whole waves reasonably,
   // BN = 128 for the N = 768 family (fewer idle SMs in the last wave).
-  const int sms = num_sms();
+  const int sms = gemm_sms();
   const int num_m = (p.M + BM - 1) / BM;
   auto eff = [&](int bn) {
     const int tiles = num_m * ((p.N + bn - 1) / bn);
@@ -574,3 +585,5 @@ int gemm_tc(const clgGemmParams& p, cudaStream_t stream) {
 }
 
 }  // namespace clg
+
+extern "C" int clg_set_gemm_sm_limit(int n) { clg::g_gemm_sm_limit = n; return CLG_OK; }

@@ -182,6 +182,11 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx=None, dx_lowp=None, dgamma=Non
     _count()
 
 
+def set_gemm_sm_limit(n: int):
+    """SMs the persistent GEMM grids occupy (0 = all); see clg_set_gemm_sm_limit"""
+    L.check(L.load().clg_set_gemm_sm_limit(int(n)), "clg_set_gemm_sm_limit")
+
+
 def set_attention_backend(backend: int):
     """0 = auto (tcgen05 for bf16), 1 = force the FFMA kernel (debug / cross-check)"""
     L.check(L.load().clg_set_attention_backend(int(backend)), "clg_set_attention_backend")

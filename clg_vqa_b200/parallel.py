@@ -166,6 +166,12 @@ def attach(model, optimizer=None, world_size: Optional[int] = None, group=None) 
         dist.broadcast(eng.p_flat, src=0, group=group)
         eng._shadow_versions = None
     ex.bind(eng)
+    if ex.world > 1 and dev.type == "cuda":
+        # leave a few SMs to NCCL: its kernels overlap the backward GEMMs, whose persistent CTAs (one per SM, static tile
+        # schedule) would otherwise queue behind them (CLG_DP_GEMM_SMS overrides; 0 = use every SM)
+        import os
+        from . import ops
+        ops.set_gemm_sm_limit(int(os.environ.get("CLG_DP_GEMM_SMS", "0")))
     if optimizer is not None:
         optimizer.grad_scale = 1.0 / ex.world
     return ex

@@ -120,6 +120,9 @@ typedef struct {
 } clgGemmParams;
 
 int clg_gemm(const clgGemmParams* p, clgStream_t stream);
+/* number of SMs the persistent tcgen05 GEMM grids occupy (0 = all).  Data parallelism leaves a few SMs to NCCL's
+ * all-reduce kernels, which otherwise delay individual persistent CTAs and with them every GEMM they overlap. */
+int clg_set_gemm_sm_limit(int n);
 size_t clg_sizeof_gemm_params(void);
 
 /* ------------------------------------------------------------------------------------------------
