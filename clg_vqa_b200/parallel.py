@@ -45,24 +45,6 @@ class GradExchange:
         self.pending.append(w)
         self.done_ranges.append((start, end))
 
-    def exchange_rows(self, ids: torch.Tensor, rows: torch.Tensor, replay: Callable[[torch.Tensor, torch.Tensor], None]):
-        """all-gather (ids [n], rows [n, d]) and call replay(ids_r, rows_r) for every OTHER rank r.
-        All ranks must pass the same n."""
-        if not self.enabled or self.world == 1:
-            return
-        ids = ids.contiguous()
-        rows = rows.contiguous()
-        all_ids = torch.empty(self.world * ids.numel(), dtype=ids.dtype, device=ids.device)
-        all_rows = torch.empty(self.world * rows.numel(), dtype=rows.dtype, device=rows.device)
-        dist.all_gather_into_tensor(all_ids, ids.reshape(-1), group=self.group)
-        dist.all_gather_into_tensor(all_rows, rows.reshape(-1), group=self.group)
-        all_ids = all_ids.view((self.world,) + tuple(ids.shape))
-        all_rows = all_rows.view((self.world,) + tuple(rows.shape))
-        me = dist.get_rank(self.group)
-        for r in range(self.world):
-            if r != me:
-                replay(all_ids[r], all_rows[r])
-
     def add_rows(self, ids: torch.Tensor, rows: torch.Tensor):
         """word-table gradient rows of one backward (kept until the next exchange; micro-steps inside no_sync() pile up)"""
         ids, rows = ids.reshape(-1), rows.reshape(ids.numel(), -1)

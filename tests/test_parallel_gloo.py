@@ -1,6 +1,6 @@
 """CPU, world_size = 2, gloo: the data-parallel gradient exchange (clg_vqa_b200.parallel.GradExchange).
 N-rank result must equal the single-process result on the concatenated batch: dense ranges are
-sum-all-reduced in place, the word-embedding gradient is exchanged as (token ids, rows) and replayed,
+sum-all-reduced in place, the word-embedding gradient is exchanged as (token ids, rows) and reduced from one list,
 no_sync() suppresses communication during gradient accumulation."""
 import os
 import socket
@@ -37,7 +37,9 @@ def _worker(rank, world, port, out):
         ex.reduce_range(mine_dense, 2048, 3072)
         ex.reduce_range(mine_dense, 0, 1024)
         ex.reduce_range(mine_dense, 3072, 4096)
-        ex.exchange_rows(ids, rows, lambda i, r: table.index_add_(0, i, r))
+        table.zero_()                                           # data-parallel mode: the rank does not scatter its own rows
+        ex.add_rows(ids, rows)
+        ex.exchange_rows_deterministic(lambda i, r: table.index_add_(0, i, r))
         ex.finish()
         # reference: gather everything and sum
         all_dense = [torch.zeros_like(dense) for _ in range(world)]
