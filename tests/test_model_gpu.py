@@ -241,3 +241,35 @@ def test_uc2_sft_masks_match_reference_golden(precision):
     if precision == "fp32":
         ref = torch.from_numpy(g["grad::" + qn + "[:8]"])
         assert _rel(gq[:8], ref) <= 2e-4
+
+
+def test_packed_rows_equal_padded_rows():
+    """Dropping the masked positions before the encoder layers (engine._forward, CLG_PACK) must not change anything that is
+    observable: same logits / loss / gradients as the padded computation up to the accumulation-order noise of the bf16
+    pipeline (the keys sit at different K positions of the P V product), and identical answer argmax on safe margins."""
+    g, meta = _load_golden("uc2_L2_B4")
+    b = _batch(meta)
+    outs = {}
+    for pack in (True, False):
+        model, cfg, task_cfg = _build_uc2(meta, "bf16")
+        model.engine.pack_enabled = pack
+        loss, score = TU.ForwardModelsTrain(cfg, task_cfg, DEV, "TASK15", S.batch_tuple(b), model)
+        loss.backward()
+        with torch.no_grad():
+            logits = _fwd(model, b).clone()
+        grads = {n: p.grad.detach().double().clone() for n, p in model.named_parameters() if p.grad is not None}
+        outs[pack] = (logits, float(loss), grads)
+    lp, ll, gp = outs[True]
+    lu, lo, gu = outs[False]
+    assert _rel(lp, lu) <= 5e-3
+    assert abs(ll - lo) / lo <= 1e-3
+    ref = torch.from_numpy(g["logits_bf16shim"])
+    margin = torch.topk(ref, 2, dim=1).values
+    safe = (margin[:, 0] - margin[:, 1]) > 2e-3 * ref.abs().max()
+    assert torch.equal(lp.argmax(1).cpu()[safe], lu.argmax(1).cpu()[safe])
+    floor = float(np.median(g["grad_norms"]))
+    for n in gu:
+        assert abs(float(gp[n].norm()) - float(gu[n].norm())) / max(float(gu[n].norm()), floor) <= 5e-2, n
+    # the masked text rows of the word-embedding gradient are exactly zero in both
+    wg = gp["bert.embeddings.word_embeddings.weight"]
+    assert torch.equal(torch.nonzero(wg.abs().sum(1) > 0).flatten().cpu(), torch.from_numpy(g["wordgrad_rows"]))
