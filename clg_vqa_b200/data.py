@@ -13,6 +13,40 @@ from typing import Iterable, Iterator, Tuple
 import torch
 
 
+class LabelPriorTable:
+    """The label-prior distance rows of a batch from a table that lives on the device.
+
+    The reference builds `semantic_distance[b, j] = semantic_dict[(j, t_b)]` (0 for j == t_b) with a Python double loop over
+    B x 1842 dictionary look-ups per batch and ships the fp32 [B, 1842] matrix to the GPU with every batch
+    (datasets/gqa_dataset_semantic_code_mix.py:L371-381, L433).  The table is 1842 x 1842 fp32 = 13.6 MB: keep it resident
+    and gather the B rows by label (`clg_rows_gather`); the batch then only carries the B labels.
+    """
+
+    def __init__(self, table: torch.Tensor, device):
+        """table[t, j] = distance of answer j from target answer t (diagonal 0), shape [A, A]"""
+        if table.dim() != 2 or table.shape[0] != table.shape[1]:
+            raise ValueError("expected a square [num_labels, num_labels] table")
+        self.table = table.to(device=device, dtype=torch.float32).contiguous()
+
+    @classmethod
+    def from_semantic_dict(cls, semantic_dict, num_labels: int, device):
+        """semantic_dict[(j, t)] as loaded by the reference's dataset (missing pairs and the diagonal are 0)"""
+        t = torch.zeros(num_labels, num_labels, dtype=torch.float32)
+        for (j, tt), v in semantic_dict.items():
+            if j != tt and 0 <= j < num_labels and 0 <= tt < num_labels:
+                t[tt, j] = float(v)
+        return cls(t, device)
+
+    def rows(self, labels: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """[B, A] distances for the B target labels (int64 / int32, on the table's device or on the host)"""
+        from . import ops
+        idx = labels.reshape(-1).to(device=self.table.device, dtype=torch.int32, non_blocking=True)
+        if out is None:
+            out = torch.empty(idx.numel(), self.table.shape[1], dtype=torch.float32, device=self.table.device)
+        ops.rows_gather(self.table, idx, out)
+        return out
+
+
 class DevicePrefetcher:
     """Iterates over an iterable of tuples of pinned host tensors, yielding tuples of device tensors.
 

@@ -25,3 +25,22 @@ def test_prefetcher_empty_and_single():
     assert list(DevicePrefetcher(iter([]), "cuda")) == []
     out = list(DevicePrefetcher(iter([(torch.ones(8).pin_memory(),)]), "cuda"))
     assert len(out) == 1 and float(out[0][0].sum()) == 8.0
+
+
+def test_label_prior_table_rows():
+    """device-resident label-prior table: rows gathered by label equal the reference's per-batch dictionary look-ups"""
+    from clg_vqa_b200.data import LabelPriorTable
+    A = 1842
+    g = torch.Generator().manual_seed(1)
+    sem = {}
+    for _ in range(5000):
+        j, t = int(torch.randint(0, A, (1,), generator=g)), int(torch.randint(0, A, (1,), generator=g))
+        sem[(j, t)] = float(torch.rand(1, generator=g)) * 1.2
+    tab = LabelPriorTable.from_semantic_dict(sem, A, "cuda")
+    labels = torch.randint(0, A, (64,), generator=g)
+    rows = tab.rows(labels).cpu()
+    for b in range(64):
+        t = int(labels[b])
+        for j in (0, 1, t, A - 1, int(torch.randint(0, A, (1,), generator=g))):
+            want = 0.0 if j == t else sem.get((j, t), 0.0)
+            assert abs(float(rows[b, j]) - want) < 1e-7
