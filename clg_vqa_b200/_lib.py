@@ -41,6 +41,10 @@ class GemmParams(C.Structure):
         ("dropout", Dropout),
         ("backend", c_i32), ("split_k", c_i32),
         ("colsum", c_vp),
+        ("A2", c_vp), ("B2", c_vp), ("C2", c_vp),
+        ("lda2", c_i64), ("ldb2", c_i64), ("ldc2", c_i64),
+        ("mask_bits2", c_vp),
+        ("M2", c_i32), ("_pad2", c_i32),
     ]
 
 

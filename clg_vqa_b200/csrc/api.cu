@@ -91,6 +91,22 @@ int clg_gemm(const clgGemmParams* p, clgStream_t stream) {
   int st = clg::require_sm100();
   if (st != CLG_OK) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->M2 > 0) {
+    // two row groups: one tensor-core launch when the tiling allows it, else the two GEMMs one after the other
+    if (!p->A2 || !p->B2 || !p->C2) return CLG_ERR_ARG;
+    if (p->backend != CLG_GEMM_SIMT && p->a_dtype == CLG_BF16 && p->b_dtype == CLG_BF16 && p->K >= 64) {
+      st = clg::gemm_tc(*p, s);
+      if (st != CLG_ERR_UNSUPPORTED) return st;
+    }
+    clgGemmParams g1 = *p, g2 = *p;
+    g1.M2 = 0;
+    g2.M2 = 0;
+    g2.A = p->A2; g2.B = p->B2; g2.C = p->C2;
+    g2.lda = p->lda2; g2.ldb = p->ldb2; g2.ldc = p->ldc2;
+    g2.mask_bits = p->mask_bits2; g2.M = p->M2;
+    st = clg_gemm(&g1, stream);
+    return st != CLG_OK ? st : clg_gemm(&g2, stream);
+  }
   if (p->backend == CLG_GEMM_SIMT) return clg::gemm_simt(*p, s);
   if (p->backend == CLG_GEMM_TC) return clg::gemm_tc(*p, s);
   // auto: tensor cores for bf16 x bf16 problems that are big enough to tile, FFMA otherwise

@@ -19,6 +19,8 @@ struct EpiArgs {
   int drop_before_act;
   Drop drop;
   float* colsum;      // optional [N]: += column sums of the epilogue result
+  // second row group (see clgGemmParams): its output, mask and row count
+  void* C2; int64_t ldc2; const uint32_t* mask_bits2; int M2;
 };
 
 inline EpiArgs make_epi(const clgGemmParams& p) {
@@ -36,6 +38,7 @@ inline EpiArgs make_epi(const clgGemmParams& p) {
   e.drop_before_act = p.drop_before_act;
   e.drop = make_drop(p.dropout);
   e.colsum = p.colsum;
+  e.C2 = p.C2; e.ldc2 = p.ldc2; e.mask_bits2 = p.mask_bits2; e.M2 = p.M2;
   return e;
 }
 

@@ -50,6 +50,7 @@ struct TcArgs {
   int num_m, num_n, splits, kper, kblocks;
   int staged;      // epilogue may use the coalesced shared-memory staged path
   int total_units; // work units: (m block | pair of m blocks when MC) x n block x split
+  int m_split_blk; // first 128-row block of the second row group (0: no second group)
 };
 
 // MC: clusters of two CTAs work on two vertically adjacent 128-row tiles of the same N block; each CTA loads
@@ -59,6 +60,7 @@ template <int BN, bool A_K, bool B_K, int MC, int EPI>
 __global__ void __launch_bounds__(num_threads<EPI>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_x,
+               const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_b2,
                const TcArgs t, const EpiArgs e) {
   using Cfg = TileCfg<BN, EPI, MC>;
   constexpr int KSTAGES = Cfg::KSTAGES;
@@ -87,6 +89,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    if (t.m_split_blk > 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a2)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b2)) : "memory");
+    }
     for (int s = 0; s < KSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), MC == 1 ? 2 : 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), (MC == 2 ? 2 : 1) * epi_warps<EPI>()); }
     for (int s = 0; s < 2 * epi_warps<EPI>(); ++s) mbar_init(epi_in_bar + 8u * s, 1);
@@ -120,7 +126,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     for (int w = w_first; w < total_work; w += w_step) {
       const int split = w % t.splits;
       const int tile = w / t.splits;
-      const int n_blk = tile % t.num_n, m_blk = m_block_of(tile);
+      const int n_blk = tile % t.num_n;
+      int m_blk = m_block_of(tile);
+      // second row group: its own operands, rows counted from its first block
+      const bool g2 = t.m_split_blk > 0 && m_blk >= t.m_split_blk;
+      const CUtensorMap* pa = g2 ? &tma_a2 : &tma_a;
+      const CUtensorMap* pb = g2 ? &tma_b2 : &tma_b;
+      if (g2) m_blk -= t.m_split_blk;
       const int kb0 = split * t.kper;
       const int kb1 = min(t.kblocks, kb0 + t.kper);
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -133,18 +145,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
             const uint32_t sb = sa + A_TILE_BYTES;
             if (A_K) {
-              tma_load_2d_2cta(sa, &tma_a, fb, kb * BK, m_blk * BM);
+              tma_load_2d_2cta(sa, pa, fb, kb * BK, m_blk * BM);
             } else {
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j)
-                tma_load_2d_2cta(sa + j * (64 * BK * 2), &tma_a, fb, m_blk * BM + j * 64, kb * BK);
+                tma_load_2d_2cta(sa + j * (64 * BK * 2), pa, fb, m_blk * BM + j * 64, kb * BK);
             }
             if (B_K) {
-              tma_load_2d_2cta(sb, &tma_b, fb, kb * BK, n_blk * BN + crank * (BN / 2));
+              tma_load_2d_2cta(sb, pb, fb, kb * BK, n_blk * BN + crank * (BN / 2));
             } else {
 #pragma unroll
               for (int j = 0; j < BN / 128; ++j)
-                tma_load_2d_2cta(sb + j * (64 * BK * 2), &tma_b, fb, n_blk * BN + (crank * (BN / 128) + j) * 64, kb * BK);
+                tma_load_2d_2cta(sb + j * (64 * BK * 2), pb, fb, n_blk * BN + (crank * (BN / 128) + j) * 64, kb * BK);
             }
           }
         } else if (elect_one()) {
@@ -152,29 +164,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + A_TILE_BYTES;
           if (A_K) {
-            tma_load_2d(sa, &tma_a, full_bar(stage), kb * BK, m_blk * BM);
+            tma_load_2d(sa, pa, full_bar(stage), kb * BK, m_blk * BM);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sa + j * (64 * BK * 2), &tma_a, full_bar(stage), m_blk * BM + j * 64, kb * BK);
+              tma_load_2d(sa + j * (64 * BK * 2), pa, full_bar(stage), m_blk * BM + j * 64, kb * BK);
           }
           if (MC == 1) {
             // this CTA fetches its half of the B tile and multicasts it to both CTAs of the pair
             if (B_K) {
-              tma_load_2d_mc(sb + crank * (BN / 2) * 128, &tma_b, full_bar(stage), kb * BK, n_blk * BN + crank * (BN / 2), 3);
+              tma_load_2d_mc(sb + crank * (BN / 2) * 128, pb, full_bar(stage), kb * BK, n_blk * BN + crank * (BN / 2), 3);
             } else {
 #pragma unroll
               for (int j = 0; j < BN / 128; ++j) {
                 const int jj = crank * (BN / 128) + j;
-                tma_load_2d_mc(sb + jj * (64 * BK * 2), &tma_b, full_bar(stage), n_blk * BN + jj * 64, kb * BK, 3);
+                tma_load_2d_mc(sb + jj * (64 * BK * 2), pb, full_bar(stage), n_blk * BN + jj * 64, kb * BK, 3);
               }
             }
           } else if (B_K) {
-            tma_load_2d(sb, &tma_b, full_bar(stage), kb * BK, n_blk * BN);
+            tma_load_2d(sb, pb, full_bar(stage), kb * BK, n_blk * BN);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * (64 * BK * 2), &tma_b, full_bar(stage), n_blk * BN + j * 64, kb * BK);
+              tma_load_2d(sb + j * (64 * BK * 2), pb, full_bar(stage), n_blk * BN + j * 64, kb * BK);
           }
         }
         __syncwarp();
@@ -236,10 +248,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if constexpr (EPI == EPI_GENERIC) {
       // generic form: interleaved over the 32-column chunks of the tile, staged through a [32][33] fp32 tile
       float* stg = reinterpret_cast<float*>(smem_gen + KSTAGES * Cfg::STAGE_BYTES) + (warp - 2) * STG_FLOATS;
+      EpiArgs e2 = e;                      // the second row group's view of the epilogue
+      e2.C = e.C2; e2.ldc = e.ldc2; e2.mask_bits = e.mask_bits2; e2.M = e.M2;
       int local = 0;
       for (int w = w_first; w < total_work; w += w_step, ++local) {
         const int tile = w / t.splits;
-        const int n_blk = tile % t.num_n, m_blk = m_block_of(tile);
+        const int n_blk = tile % t.num_n;
+        int m_blk = m_block_of(tile);
+        const bool g2 = t.m_split_blk > 0 && m_blk >= t.m_split_blk;
+        if (g2) m_blk -= t.m_split_blk;
+        const EpiArgs& eg = g2 ? e2 : e;
         const int as = local & 1;
         const uint32_t aphase = (local >> 1) & 1;
         mbar_wait(tfull_bar(as), aphase);
@@ -251,7 +269,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int c = half; c < BN / 32; c += 2) {
           float v[32];
           tmem_ld32(taddr + (uint32_t)(c * 32), v);
-          tc_epi_chunk(e, stg, r0, n_blk * BN + c * 32, lane, t.staged != 0, v);
+          tc_epi_chunk(eg, stg, r0, n_blk * BN + c * 32, lane, t.staged != 0, v);
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -415,6 +433,17 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
   if (B_K) st = make_tmap_bf16(&tb, p.B, p.K, p.N, p.ldb, MC ? BN / 2 : BN);
   else     st = make_tmap_bf16(&tb, p.B, p.N, p.K, p.ldb, BK);
   if (st != CLG_OK) return st;
+  CUtensorMap ta2 = ta, tb2 = tb;
+  const bool grouped = p.M2 > 0;
+  if (grouped) {
+    if (EPI != EPI_GENERIC || !MC || (p.M % (2 * BM)) != 0 || !p.A2 || !p.B2 || !p.C2) return CLG_ERR_ARG;
+    if (A_K) st = make_tmap_bf16(&ta2, p.A2, p.K, p.M2, p.lda2, BM);
+    else     st = make_tmap_bf16(&ta2, p.A2, p.M2, p.K, p.lda2, BK);
+    if (st != CLG_OK) return st;
+    if (B_K) st = make_tmap_bf16(&tb2, p.B2, p.K, p.N, p.ldb2, MC ? BN / 2 : BN);
+    else     st = make_tmap_bf16(&tb2, p.B2, p.N, p.K, p.ldb2, BK);
+    if (st != CLG_OK) return st;
+  }
   if (EPI != EPI_GENERIC) {
     st = make_tmap_epi(&tc, p.C, p.c_dtype, p.N, p.M, p.ldc);
     if (st != CLG_OK) return st;
@@ -429,7 +458,8 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
 
   TcArgs t;
   t.M = p.M; t.N = p.N; t.K = p.K;
-  t.num_m = (p.M + BM - 1) / BM;
+  t.m_split_blk = grouped ? p.M / BM : 0;
+  t.num_m = (p.M + BM - 1) / BM + (grouped ? (p.M2 + BM - 1) / BM : 0);
   t.num_n = (p.N + BN - 1) / BN;
   t.kblocks = (p.K + BK - 1) / BK;
   const int sms = gemm_sms();
@@ -460,10 +490,18 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
       // split-K accumulates atomically: C must start from zero
       CLG_CUDA_OK(cudaMemset2DAsync(p.C, p.ldc * sizeof(float), 0, (size_t)p.N * sizeof(float), p.M, stream),
                   "memset(split-K C)");
+      if (grouped)
+        CLG_CUDA_OK(cudaMemset2DAsync(p.C2, p.ldc2 * sizeof(float), 0, (size_t)p.N * sizeof(float), p.M2, stream),
+                    "memset(split-K C2)");
     }
     e.accumulate = 2;
   }
   t.staged = (epi_can_stage(e) && (p.N % 2 == 0)) ? 1 : 0;
+  if (grouped && t.staged) {
+    EpiArgs e2 = e;
+    e2.C = e.C2; e2.ldc = e.ldc2;
+    if (!epi_can_stage(e2)) t.staged = 0;
+  }
   if (MC) {
     t.total_units = ((t.num_m + 1) / 2) * t.num_n * t.splits;
     const int max_clusters = sms / 2;
@@ -479,13 +517,13 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    CLG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_K, B_K, MC, EPI>, ta, tb, tc, tx, t, e),
+    CLG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_K, B_K, MC, EPI>, ta, tb, tc, tx, ta2, tb2, t, e),
                 "cudaLaunchKernelEx(gemm_tc, cluster 2)");
     return check_launch("gemm_tc_kernel(mc)");
   }
   t.total_units = t.num_m * t.num_n * t.splits;
   const int grid = t.total_units < sms ? t.total_units : sms;
-  CLG_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, A_K, B_K, MC, EPI>, dim3(grid), dim3(num_threads<EPI>()), Cfg::SMEM_BYTES, stream, ta, tb, tc, tx, t, e),
+  CLG_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, A_K, B_K, MC, EPI>, dim3(grid), dim3(num_threads<EPI>()), Cfg::SMEM_BYTES, stream, ta, tb, tc, tx, ta2, tb2, t, e),
               "launch(gemm_tc)");
   return check_launch("gemm_tc_kernel");
 }
@@ -526,9 +564,10 @@ static int dispatch_major(const clgGemmParams& p, const EpiArgs& e, cudaStream_t
   // pairs of vertically adjacent tiles share the B tile through TMA multicast whenever there are at least two
   // row blocks (BN >= 128 so that each CTA's half of an MN-major B tile is a whole 64-wide box)
   const bool mc = BN >= 128 && p.M > BM && multicast_enabled();
+  if (p.M2 > 0 && !mc) return CLG_ERR_UNSUPPORTED;
   if (mc) {
     constexpr int BNF = BN >= 128 ? BN : 128;
-    if (p.a_kmajor && p.split_k <= 1 && fast_epilogue_enabled()) {
+    if (p.M2 <= 0 && p.a_kmajor && p.split_k <= 1 && fast_epilogue_enabled()) {
       const int kind = classify_epilogue(e);
       if (kind != EPI_GENERIC) return dispatch_fast<BNF>(kind, p, e, s);
     }
@@ -545,7 +584,8 @@ int gemm_tc(const clgGemmParams& p, cudaStream_t stream) {
   // Tile choice: BN = 256 when the tile count still fills the machine in whole waves reasonably,
   // BN = 128 for the N = 768 family (fewer idle SMs in the last wave).
   const int sms = gemm_sms();
-  const int num_m = (p.M + BM - 1) / BM;
+  if (p.M2 > 0 && ((p.M % (2 * BM)) != 0 || p.N < 128)) return CLG_ERR_UNSUPPORTED;
+  const int num_m = (p.M + BM - 1) / BM + (p.M2 > 0 ? (p.M2 + BM - 1) / BM : 0);
   auto eff = [&](int bn) {
     const int tiles = num_m * ((p.N + bn - 1) / bn);
     const int waves = (tiles + sms - 1) / sms;

@@ -88,6 +88,7 @@ class Engine:
         self.step_counter = 0
         self.grads_consumed = True       # True: next backward zeroes the gradient arena first
         self.pack_enabled = os.environ.get("CLG_PACK", "1") != "0"   # drop masked positions before the encoder layers
+        self.group_wgrad = os.environ.get("CLG_GROUP_WGRAD", "1") != "0"   # QKV + attention-output weight gradients in one launch
         self.dp = None                   # optional parallel.GradExchange
         self.L = cfgmod.num_encoder_layers(self.cfg)
         self.d = self.cfg.hidden_size
@@ -658,6 +659,13 @@ class Engine:
         ops.gemm(a, b, self._g(s, rows, cols), a_kmajor=False, b_kmajor=False, accumulate=True,
                  mask_bits=self._wmask(mod0), K=tokens)
 
+    def _wgrad2(self, a, b, mod0, rows, cols, a2, b2, mod2, rows2, tokens=None):
+        """Two weight gradients with the same input width in one launch (rows % 256 == 0): together the QKV and
+        attention-output gradients have the tile count of one FFN gradient, which fills the machine."""
+        ops.gemm(a, b, self._g(self.w_slot[id(mod0)], rows, cols), a_kmajor=False, b_kmajor=False, accumulate=True,
+                 mask_bits=self._wmask(mod0), K=tokens,
+                 group2=(a2, b2, self._g(self.w_slot[id(mod2)], rows2, cols), self._wmask(mod2)))
+
     def _head_bwd(self, ws, sv, dl, x_lp, pmod, pool_dact, site_pool):
         d = self.d
         B, S = sv["B"], sv["T"] + sv["R"]
@@ -724,12 +732,17 @@ class Engine:
         ops.layernorm_bwd(dx, lw["y1"], ln1.weight.data, lw["m1"], lw["r1"], dx=dy, dx_lowp=dgo,
                           dgamma=self.grad_view(ln1.weight), dbeta=self.grad_view(ln1.bias),
                           dbias=self._gvec(self.b_slot[id(omod)], d), dropout_in=site_o, rows=M)
-        self._wgrad(dgo, lw["ctx"], omod, d, d, tokens=M)
+        grouped = self.group_wgrad and ws["lp"] == torch.bfloat16 and (3 * d) % 256 == 0
+        if not grouped:
+            self._wgrad(dgo, lw["ctx"], omod, d, d, tokens=M)
         ops.gemm(dgo, self._w(omod, d, d), ws["dctx"], b_kmajor=False, M=M)
         ops.attention_bwd(lw["qkv"], kb, lw["ctx"], ws["dctx"], lw["lse"], ws["dqkv"], B, S, H, scale, site_p,
                           cu_rows=cu, total_rows=M if cu is not None else 0)
         ops.colsum(ws["dqkv"], self._gvec(self.b_slot[id(qmod)], 3 * d), M=M)
-        self._wgrad(ws["dqkv"], x_in_lp, qmod, 3 * d, d, tokens=M)
+        if grouped:     # dgo still holds the attention-output operand: nothing between LN1's backward and here writes it
+            self._wgrad2(ws["dqkv"], x_in_lp, qmod, 3 * d, d, dgo, lw["ctx"], omod, d, tokens=M)
+        else:
+            self._wgrad(ws["dqkv"], x_in_lp, qmod, 3 * d, d, tokens=M)
         ops.gemm(ws["dqkv"], self._w(qmod, 3 * d, d), dx, b_kmajor=False, residual=dy, M=M)
 
     def _backward_uc2(self, dl, sv):

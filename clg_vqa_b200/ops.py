@@ -81,7 +81,7 @@ def _ld(t: torch.Tensor) -> int:
 
 def gemm(a, b, c, *, a_kmajor=True, b_kmajor=True, M=None, N=None, K=None, alpha=1.0, act=ACT_NONE, bias=None,
          residual=None, aux_in=None, aux_out=None, mask_bits=None, accumulate=False, dropout: DropSite = NO_DROP,
-         drop_before_act=False, backend=GEMM_AUTO, split_k=0, colsum=None):
+         drop_before_act=False, backend=GEMM_AUTO, split_k=0, colsum=None, group2=None):
     """C[M,N] = epi(alpha * A(m,k) B(n,k)).  a: [M,K] if a_kmajor else [K,M]; b: [N,K] if b_kmajor else [K,N]."""
     _need_cuda(a, b, c)
     if M is None:
@@ -110,6 +110,13 @@ def gemm(a, b, c, *, a_kmajor=True, b_kmajor=True, M=None, N=None, K=None, alpha
     p.dropout = dropout.c()
     p.backend, p.split_k = int(backend), int(split_k)
     p.colsum = _ptr(colsum)
+    if group2 is not None:          # (a2, b2, c2, mask_bits2): a second GEMM of the same N, K and options stacked under this one
+        a2, b2, c2, mb2 = group2
+        _need_cuda(a2, b2, c2)
+        p.A2, p.B2, p.C2 = a2.data_ptr(), b2.data_ptr(), c2.data_ptr()
+        p.lda2, p.ldb2, p.ldc2 = _ld(a2), _ld(b2), _ld(c2)
+        p.mask_bits2 = _ptr(mb2)
+        p.M2 = int(a2.shape[0] if a_kmajor else a2.shape[1])
     rec = _gemm_timing
     if rec is not None:
         # same predicate as clg_gemm's auto dispatch: these launches run gemm_tc_kernel
@@ -121,7 +128,7 @@ def gemm(a, b, c, *, a_kmajor=True, b_kmajor=True, M=None, N=None, K=None, alpha
             e0.record()
             L.check(L.load().clg_gemm(C.byref(p), _stream()), "clg_gemm")
             e1.record()
-            rec.append((e0, e1, 2.0 * M * N * K))
+            rec.append((e0, e1, 2.0 * (M + int(p.M2)) * N * K))
             _count()
             return c
     L.check(L.load().clg_gemm(C.byref(p), _stream()), "clg_gemm")

@@ -117,6 +117,15 @@ typedef struct {
   int32_t split_k;         /* 0 = auto (TC backend, act==NONE && no bias only) */
   float* colsum;           /* optional [N]: colsum[n] += sum_m (epilogue result, before rounding to c_dtype); the bias
                               gradient of the layer that produced A's pre-activation, fused into the dgrad GEMM */
+  /* Optional second group, row-concatenated under the first (M2 > 0): rows [M, M + M2) of the virtual output are
+   * C2 = epi(A2 B2^T) with the same N, K, dtypes, major-ness and epilogue options but their own operands, output and
+   * mask.  M must be a multiple of 256.  One launch then fills the machine where two small GEMMs could not: the QKV
+   * (2304 x 768) and attention-output (768 x 768) weight gradients of a layer together have the tile count of one FFN
+   * weight gradient. */
+  const void* A2; const void* B2; void* C2;
+  int64_t lda2, ldb2, ldc2;
+  const uint32_t* mask_bits2;
+  int32_t M2; int32_t _pad2;
 } clgGemmParams;
 
 int clg_gemm(const clgGemmParams* p, clgStream_t stream);

@@ -136,3 +136,38 @@ def test_large_m_residual_dropout_all_rows():
     ops.gemm(a, w, ref, bias=bias, residual=res, dropout=site, backend=ops.GEMM_SIMT)
     assert _rel(y, ref) < 2e-5
     assert _rel(y[-300:], ref[-300:]) < 2e-5
+
+
+@pytest.mark.parametrize("M1,M2,N,K,akm", [(2304, 768, 768, 7000, False), (2304, 768, 768, 9216, False), (512, 200, 256, 640, False),
+                                           (256, 129, 384, 192, True), (2304, 768, 768, 100, False), (300, 200, 256, 640, False)])
+def test_two_row_groups_match_separate_launches(M1, M2, N, K, akm):
+    """clgGemmParams.A2/B2/C2: the second GEMM stacked under the first gives what two launches give -- fp32 accumulate
+    into existing gradients, each group with its own sparse-fine-tuning mask; the last two shapes take the fallback
+    (two launches inside clg_gemm: K < 64, M1 not a multiple of 256)."""
+    def operand(rows, seed):
+        return _rand(rows, K, dtype=torch.bfloat16, seed=seed) if akm else _rand(K, rows, dtype=torch.bfloat16, seed=seed)
+    a1, a2 = operand(M1, 1), operand(M2, 2)
+    b1 = _rand(K, N, dtype=torch.bfloat16, scale=0.1, seed=3)
+    b2 = _rand(K, N, dtype=torch.bfloat16, scale=0.1, seed=4)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    bits1 = torch.randint(-2**31, 2**31 - 1, ((M1 * N + 31) // 32,), generator=g, dtype=torch.int32).to(DEV)
+    bits2 = torch.randint(-2**31, 2**31 - 1, ((M2 * N + 31) // 32,), generator=g, dtype=torch.int32).to(DEV)
+    for masks in ((None, None), (bits1, bits2)):
+        c1, c2 = _rand(M1, N, seed=6), _rand(M2, N, seed=7)
+        r1, r2 = c1.clone(), c2.clone()
+        ops.gemm(a1, b1, c1, a_kmajor=akm, b_kmajor=False, accumulate=True, mask_bits=masks[0],
+                 group2=(a2, b2, c2, masks[1]))
+        ops.gemm(a1, b1, r1, a_kmajor=akm, b_kmajor=False, accumulate=True, mask_bits=masks[0])
+        ops.gemm(a2, b2, r2, a_kmajor=akm, b_kmajor=False, accumulate=True, mask_bits=masks[1])
+        ref1 = (a1.double() if akm else a1.double().t()) @ b1.double()
+        ref2 = (a2.double() if akm else a2.double().t()) @ b2.double()
+        assert _rel(c1, r1) < 2e-5 and _rel(c2, r2) < 2e-5
+        if masks[0] is None:
+            assert _rel(c1 - _rand(M1, N, seed=6), ref1) < 2e-4 and _rel(c2 - _rand(M2, N, seed=7), ref2) < 2e-4
+        else:       # masked-out entries: identical positions in both forms
+            assert torch.equal(c1 == 0, r1 == 0) and torch.equal(c2 == 0, r2 == 0)
+    # without accumulate the split-K path zeroes both outputs first
+    c1 = torch.full((M1, N), float("nan"), device=DEV)
+    c2 = torch.full((M2, N), float("nan"), device=DEV)
+    ops.gemm(a1, b1, c1, a_kmajor=akm, b_kmajor=False, group2=(a2, b2, c2, None))
+    assert _rel(c1, ref1) < 2e-4 and _rel(c2, ref2) < 2e-4
