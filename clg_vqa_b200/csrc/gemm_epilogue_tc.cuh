@@ -167,19 +167,41 @@ __device__ __forceinline__ void stage_store_any(float* stg, void* g, int dtype, 
   else stage_store<float>(stg, (float*)g, ld, r0, c0, M, lane, v, accumulate);
 }
 
-// true when every tensor of the epilogue can use 16 B row-coalesced accesses for full 32-column chunks
-__host__ inline bool epi_can_stage(const EpiArgs& e) {
+// fp32 output whose rows are not 16 B aligned (the 1842-wide GQA logits): one column per lane, a 128 B row per instruction
+__device__ __forceinline__ void stage_store_lanes(float* stg, float* g, int64_t ld, int r0, int c0, int M, int lane,
+                                                  const float* v, int accumulate) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) stg[lane * STG_LD + j] = v[j];
+  __syncwarp();
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    if (r0 + r >= M) break;
+    const float f = stg[r * STG_LD + lane];
+    float* p = g + (int64_t)(r0 + r) * ld + c0 + lane;
+    if (accumulate == 2) atomicAdd(p, f);
+    else *p = accumulate == 1 ? *p + f : f;
+  }
+  __syncwarp();
+}
+
+// 1: every tensor of the epilogue can use 16 B row-coalesced accesses for full 32-column chunks; 2: all but an fp32
+// output with unaligned rows, which is stored one column per lane; 0: per-thread path
+__host__ inline int epi_stage_mode(const EpiArgs& e) {
   auto ok = [](const void* p, int64_t ld, int dtype) {
     if (!p) return true;
     const int64_t m = dtype == CLG_BF16 ? 8 : 4;
     return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld % m) == 0;
   };
-  return ok(e.C, e.ldc, e.c_dtype) && ok(e.residual, e.ld_res, CLG_F32) && ok(e.aux_in, e.ld_aux_in, e.aux_in_dtype) &&
-         ok(e.aux_out, e.ld_aux_out, e.aux_out_dtype) && (!e.bias || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0);
+  if (!(ok(e.residual, e.ld_res, CLG_F32) && ok(e.aux_in, e.ld_aux_in, e.aux_in_dtype) &&
+        ok(e.aux_out, e.ld_aux_out, e.aux_out_dtype) && (!e.bias || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0)))
+    return 0;
+  if (ok(e.C, e.ldc, e.c_dtype)) return 1;
+  return e.c_dtype == CLG_F32 ? 2 : 0;
 }
+__host__ inline bool epi_can_stage(const EpiArgs& e) { return epi_stage_mode(e) == 1; }
 
 // warp-collective: rows r0 .. r0+31 (lane = row), columns c0 .. c0+31
-__device__ __forceinline__ void tc_epi_chunk(const EpiArgs& e, float* stg, int r0, int c0, int lane, bool staged, float* acc) {
+__device__ __forceinline__ void tc_epi_chunk(const EpiArgs& e, float* stg, int r0, int c0, int lane, int staged, float* acc) {
   if (!staged || c0 + 32 > e.N) {          // ragged N tail or unaligned tensors: per-thread path
     epi_row_chunk<32>(e, r0 + lane, c0, acc);
     return;
@@ -270,7 +292,8 @@ __device__ __forceinline__ void tc_epi_chunk(const EpiArgs& e, float* stg, int r
       for (int j = 0; j < 32; ++j) v[j] *= mask_bit(e.mask_bits, (int64_t)(bidx + j)) ? 1.f : 0.f;
     }
   }
-  stage_store_any(stg, e.C, e.c_dtype, e.ldc, r0, c0, e.M, lane, v, e.accumulate);
+  if (staged == 2) stage_store_lanes(stg, (float*)e.C, e.ldc, r0, c0, e.M, lane, v, e.accumulate);
+  else stage_store_any(stg, e.C, e.c_dtype, e.ldc, r0, c0, e.M, lane, v, e.accumulate);
   if (e.colsum) {
     if (row >= e.M) {
 #pragma unroll

@@ -66,9 +66,109 @@ gemm_simt_kernel(const TA* __restrict__ A, const TB* __restrict__ B, int M, int 
   for (int i = 0; i < 4; ++i) epi_row_chunk<8>(e, m0 + ty * 4 + i, n0 + tx * 8, acc[i]);
 }
 
+// One element of C through the shared scalar epilogue.
+__device__ __forceinline__ void epi_store_one(const EpiArgs& e, int row, int col, float acc) {
+  const float r = epi_scalar(e, row, col, acc);
+  if (e.colsum) atomicAdd(e.colsum + col, r);
+  const int64_t ci = (int64_t)row * e.ldc + col;
+  if (e.c_dtype == CLG_BF16) {
+    bf16* c = (bf16*)e.C;
+    c[ci] = __float2bfloat16_rn(e.accumulate ? __bfloat162float(c[ci]) + r : r);
+  } else {
+    float* c = (float*)e.C;
+    if (e.accumulate == 2) atomicAdd(c + ci, r);
+    else if (e.accumulate == 1) c[ci] += r;
+    else c[ci] = r;
+  }
+}
+
+// K <= 8, both operands K-major (the box-coordinate projection Linear(5 -> 768)): a thread keeps its output column's
+// weights in registers and walks the CTA's rows; stores are coalesced along N.  Output-bandwidth bound.
+static constexpr int SK_MAX = 8, SK_ROWS = 16;
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256)
+smallk_fwd_kernel(const TA* __restrict__ A, const TB* __restrict__ B, int M, int N, int K, int64_t lda, int64_t ldb,
+                  const EpiArgs e) {
+  __shared__ float As[SK_ROWS][SK_MAX];
+  const int r0 = blockIdx.x * SK_ROWS;
+  if (threadIdx.x < SK_ROWS * SK_MAX) {
+    const int r = threadIdx.x / SK_MAX, k = threadIdx.x % SK_MAX;
+    As[r][k] = (r0 + r < M && k < K) ? to_f32<TA>(A[(int64_t)(r0 + r) * lda + k]) : 0.f;
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += 256) {
+    float w[SK_MAX];
+#pragma unroll
+    for (int k = 0; k < SK_MAX; ++k) w[k] = k < K ? to_f32<TB>(B[(int64_t)n * ldb + k]) : 0.f;
+    const int rows = min(SK_ROWS, M - r0);
+    for (int r = 0; r < rows; ++r) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < SK_MAX; ++k)
+        if (k < K) acc = fmaf(As[r][k], w[k], acc);
+      epi_store_one(e, r0 + r, n, acc);
+    }
+  }
+}
+
+// N <= 8, both operands MN-major, long K (the weight gradient of that projection, K = region rows): a thread owns one
+// output row m (coalesced reads of A along m), a CTA a slice of K; fp32 atomics combine the slices.  Reads A once.
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256)
+smalln_wgrad_kernel(const TA* __restrict__ A, const TB* __restrict__ B, int M, int N, int K, int64_t lda, int64_t ldb,
+                    int k_per_cta, const EpiArgs e) {
+  __shared__ float Bs[64][SK_MAX];
+  const int m = blockIdx.x * 256 + threadIdx.x;
+  const int k_lo = blockIdx.y * k_per_cta, k_hi = min(K, k_lo + k_per_cta);
+  float acc[SK_MAX];
+#pragma unroll
+  for (int n = 0; n < SK_MAX; ++n) acc[n] = 0.f;
+  for (int k0 = k_lo; k0 < k_hi; k0 += 64) {
+    const int kc = min(64, k_hi - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * SK_MAX; i += 256) {
+      const int k = i / SK_MAX, n = i % SK_MAX;
+      Bs[k][n] = (k < kc && n < N) ? to_f32<TB>(B[(int64_t)(k0 + k) * ldb + n]) : 0.f;
+    }
+    __syncthreads();
+    if (m < M) {
+#pragma unroll 8
+      for (int k = 0; k < kc; ++k) {
+        const float a = to_f32<TA>(A[(int64_t)(k0 + k) * lda + m]);
+#pragma unroll
+        for (int n = 0; n < SK_MAX; ++n) acc[n] = fmaf(a, Bs[k][n], acc[n]);
+      }
+    }
+  }
+  if (m < M) {
+#pragma unroll
+    for (int n = 0; n < SK_MAX; ++n)
+      if (n < N) epi_store_one(e, m, n, acc[n]);
+  }
+}
+
 template <typename TA, typename TB>
 static int launch_simt(const clgGemmParams& p, cudaStream_t s) {
   EpiArgs e = make_epi(p);
+  const bool splittable = p.act == CLG_ACT_NONE && !p.bias && !p.residual && p.c_dtype == CLG_F32 && p.dropout.p <= 0.f && !p.colsum;
+  if (p.K <= SK_MAX && p.a_kmajor && p.b_kmajor) {
+    smallk_fwd_kernel<TA, TB><<<(p.M + SK_ROWS - 1) / SK_ROWS, 256, 0, s>>>((const TA*)p.A, (const TB*)p.B, p.M, p.N, p.K,
+                                                                             p.lda, p.ldb, e);
+    return check_launch("smallk_fwd_kernel");
+  }
+  if (p.N <= SK_MAX && !p.a_kmajor && !p.b_kmajor && splittable && p.K >= 1024) {
+    const int mblocks = (p.M + 255) / 256;
+    int slices = (4 * num_sms() + mblocks - 1) / mblocks;
+    if (slices > p.K / 32) slices = p.K / 32;
+    const int kper = (p.K + slices - 1) / slices;
+    slices = (p.K + kper - 1) / kper;
+    if (!p.accumulate)
+      CLG_CUDA_OK(cudaMemset2DAsync(p.C, p.ldc * sizeof(float), 0, (size_t)p.N * sizeof(float), p.M, s), "memset(small-N wgrad)");
+    e.accumulate = 2;
+    smalln_wgrad_kernel<TA, TB><<<dim3(mblocks, slices), 256, 0, s>>>((const TA*)p.A, (const TB*)p.B, p.M, p.N, p.K, p.lda,
+                                                                      p.ldb, kper, e);
+    return check_launch("smalln_wgrad_kernel");
+  }
   dim3 grid((p.N + SBN - 1) / SBN, (p.M + SBM - 1) / SBM);
   // split-K (atomic fp32 accumulate) for long reductions with too few output tiles (e.g. dW_loc [768 x 7])
   int splits = 1;

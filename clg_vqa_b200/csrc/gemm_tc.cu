@@ -269,7 +269,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int c = half; c < BN / 32; c += 2) {
           float v[32];
           tmem_ld32(taddr + (uint32_t)(c * 32), v);
-          tc_epi_chunk(eg, stg, r0, n_blk * BN + c * 32, lane, t.staged != 0, v);
+          tc_epi_chunk(eg, stg, r0, n_blk * BN + c * 32, lane, t.staged, v);
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -496,11 +496,12 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
     }
     e.accumulate = 2;
   }
-  t.staged = (epi_can_stage(e) && (p.N % 2 == 0)) ? 1 : 0;
+  t.staged = (p.N % 2 == 0) ? epi_stage_mode(e) : 0;
   if (grouped && t.staged) {
     EpiArgs e2 = e;
     e2.C = e.C2; e2.ldc = e.ldc2;
-    if (!epi_can_stage(e2)) t.staged = 0;
+    const int m2 = epi_stage_mode(e2);
+    if (m2 != t.staged) t.staged = (m2 == 0 || e.c_dtype != CLG_F32) ? 0 : 2;
   }
   if (MC) {
     t.total_units = ((t.num_m + 1) / 2) * t.num_n * t.splits;
@@ -616,6 +617,7 @@ int gemm_tc(const clgGemmParams& p, cudaStream_t stream) {
   static const int force_bn = [] { const char* s = getenv("CLG_GEMM_FORCE_BN"); return s ? atoi(s) : 0; }();
   if (force_bn == 256 && p.N > 128) bn = 256;
   if (force_bn == 128 && p.N > 64) bn = 128;
+  if (force_bn == 64 && p.M2 <= 0) bn = 64;
   // (A second launch with narrower units for the rows of the last, partial round was measured and dropped: the step is
   // bound by L2 -> SM operand traffic when all SMs are busy, so the few clusters of a partial round run their units
   // ~1.7x faster than a full round and the split gains nothing.)

@@ -171,3 +171,53 @@ def test_two_row_groups_match_separate_launches(M1, M2, N, K, akm):
     c2 = torch.full((M2, N), float("nan"), device=DEV)
     ops.gemm(a1, b1, c1, a_kmajor=akm, b_kmajor=False, group2=(a2, b2, c2, None))
     assert _rel(c1, ref1) < 2e-4 and _rel(c2, ref2) < 2e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,K", [(9216, 5), (1000, 7), (37, 1), (25600, 5)])
+def test_box_projection_small_k_kernels(M, K, dtype):
+    """Linear(K <= 8 -> 768) on the FFMA backend: the dedicated forward (weights in registers) and weight-gradient
+    (one pass over the row gradients) kernels against fp64, with bias, the fine-tuning mask and accumulation."""
+    N = 768
+    x = _rand(M, K, dtype=dtype, seed=1)
+    w = _rand(N, K, dtype=dtype, scale=0.3, seed=2)
+    bias = _rand(N, seed=3)
+    y = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(x, w, y, bias=bias)
+    ref = x.double() @ w.double().t() + bias.double()
+    assert _rel(y, ref) < 2e-6
+    yb = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(x, w, yb, bias=bias, act=ops.ACT_GELU)
+    assert _rel(yb, torch.nn.functional.gelu(ref)) < 8e-3
+    # weight gradient dW[N, K] += dY^T X, masked
+    dy = _rand(M, N, dtype=dtype, seed=4)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    bits = torch.randint(-2**31, 2**31 - 1, ((N * K + 31) // 32,), generator=g, dtype=torch.int32).to(DEV)
+    keep = ((bits.view(-1, 1) >> torch.arange(32, device=DEV, dtype=torch.int32)) & 1).view(-1)[:N * K].view(N, K).double()
+    dw0 = _rand(N, K, seed=6)
+    dw = dw0.clone()
+    ops.gemm(dy, x, dw, a_kmajor=False, b_kmajor=False, accumulate=True, mask_bits=bits)
+    refw = dy.double().t() @ x.double()
+    assert _rel(dw - dw0, refw * keep) < 5e-5
+    dw2 = torch.full((N, K), float("nan"), device=DEV)
+    ops.gemm(dy, x, dw2, a_kmajor=False, b_kmajor=False)
+    assert _rel(dw2, refw) < 5e-5
+
+
+def test_unaligned_fp32_output_rows():
+    """The 1842-wide GQA logits: fp32 C whose rows are not 16 B aligned takes the lane-per-column staged store."""
+    M, N, K = 256, 1842, 1536
+    a = _rand(M, K, dtype=torch.bfloat16, seed=1)
+    w = _rand(N, K, dtype=torch.bfloat16, scale=0.05, seed=2)
+    bias = _rand(N, seed=3)
+    ref = a.double() @ w.double().t() + bias.double()
+    c = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(a, w, c, bias=bias)
+    assert _rel(c, ref) < 2e-5
+    c0 = _rand(M, N, seed=4)
+    c1 = c0.clone()
+    ops.gemm(a, w, c1, bias=bias, accumulate=True)
+    assert _rel(c1 - c0, ref) < 2e-5
+    c2 = torch.full((M + 3, N), float("nan"), device=DEV)      # ragged M: rows past M stay untouched
+    ops.gemm(a[:131], w, c2[:131], bias=bias)
+    assert _rel(c2[:131], ref[:131]) < 2e-5 and bool(torch.isnan(c2[131:]).all())

@@ -60,3 +60,15 @@ run(2304, 768, 15409, a_k=False, b_k=False, cdt=torch.float32, bias=False, name=
 run(3072, 768, 15409, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="FFN1 wgrad K=15409")
 run(768, 768, 15409, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="out-proj wgrad K=15409")
 run(19456, 768, 2304, b_k=False, cdt=torch.float32, res=True, bias=False, name="QKV dgrad (+res)")
+# answer head (M = batch): latency-bound, few output tiles
+run(256, 1024, 768, cdt=torch.float32, name="head pooler fwd")
+run(256, 1536, 1024, cdt=torch.float32, name="head clf0 fwd")
+run(256, 1842, 1536, cdt=torch.float32, name="head logits fwd")
+run(256, 1536, 1848, b_k=False, cdt=torch.float32, bias=False, name="head logits dgrad")
+run(256, 1024, 1536, b_k=False, cdt=torch.float32, bias=False, name="head clf0 dgrad")
+run(256, 768, 1024, b_k=False, cdt=torch.float32, bias=False, name="head pooler dgrad")
+run(1842, 1536, 256, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="head logits wgrad")
+run(1536, 1024, 256, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="head clf0 wgrad")
+run(1024, 768, 256, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="head pooler wgrad")
+run(9216, 768, 2048, name="head image embedding fwd")
+run(768, 2048, 9216, a_k=False, b_k=False, cdt=torch.float32, bias=False, name="head image embedding wgrad")
