@@ -141,7 +141,7 @@ class AdamWParams(C.Structure):
         ("chunk_tensor", c_vp), ("tensors", c_vp), ("sumsq", c_vp),
         ("max_norm", c_f32), ("gscale", c_f32),
         ("beta1", c_f32), ("beta2", c_f32), ("eps", c_f32),
-        ("bias_c1", c_f32), ("bias_c2", c_f32), ("_pad", c_i32),
+        ("bias_c1", c_f32), ("bias_c2", c_f32), ("zero_grad", c_i32),
         ("shadow", c_vp), ("mask_bits", c_vp),
         ("hot", c_vp),
     ]

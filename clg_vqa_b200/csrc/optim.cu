@@ -70,11 +70,17 @@ adamw_kernel(const clgAdamWParams p) {
   }
   for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const int t = p.chunk_tensor[c];
-    if (t < 0) continue;
-    const clgTensorMeta tm = p.tensors[t];
     const int64_t base = c * CHUNK + (int64_t)threadIdx.x * 8;
+    const bool zero_g = UPDATE && p.zero_grad;
+    float* gz = const_cast<float*>(p.g) + base;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < 0) {                                  // no optimiser entry: its gradient (if any was written) is only cleared
+      if (zero_g) { *reinterpret_cast<float4*>(gz) = z4; *reinterpret_cast<float4*>(gz + 4) = z4; }
+      continue;
+    }
+    const clgTensorMeta tm = p.tensors[t];
     const int64_t rel = base - tm.start;          // element offset inside the tensor
-    if (rel >= tm.numel) continue;                // tail padding of the tensor's last chunk
+    if (rel >= tm.numel) continue;                // tail padding of the tensor's last chunk (never written)
     const bool cold = UPDATE && p.hot && !p.hot[base >> 8];      // warp-uniform: a warp covers one 256-element block
     if (cold && !(tm.wd > 0.f)) continue;                         // g = m = v = 0 and no decay: nothing changes
     float pv[8];
@@ -93,8 +99,8 @@ adamw_kernel(const clgAdamWParams p) {
     } else if (UPDATE) {
       float gv[8], mv[8], vv[8];
       {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p.g + base));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.g + base + 4));
+        const float4 a = *reinterpret_cast<const float4*>(p.g + base);        // plain loads: g may be cleared below
+        const float4 b = *reinterpret_cast<const float4*>(p.g + base + 4);
         gv[0] = a.x; gv[1] = a.y; gv[2] = a.z; gv[3] = a.w; gv[4] = b.x; gv[5] = b.y; gv[6] = b.z; gv[7] = b.w;
         const float4 c0 = *reinterpret_cast<const float4*>(p.m + base);
         const float4 c1 = *reinterpret_cast<const float4*>(p.m + base + 4);
@@ -121,6 +127,7 @@ adamw_kernel(const clgAdamWParams p) {
       *reinterpret_cast<float4*>(p.m + base + 4) = make_float4(mv[4], mv[5], mv[6], mv[7]);
       *reinterpret_cast<float4*>(p.v + base) = make_float4(vv[0], vv[1], vv[2], vv[3]);
       *reinterpret_cast<float4*>(p.v + base + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
+      if (zero_g) { *reinterpret_cast<float4*>(gz) = z4; *reinterpret_cast<float4*>(gz + 4) = z4; }   // after every load
     }
     if (p.shadow && tm.shadow_off >= 0) {
       if (tm.mask_off >= 0) {

@@ -90,6 +90,7 @@ class Engine:
         self.pack_enabled = os.environ.get("CLG_PACK", "1") != "0"   # drop masked positions before the encoder layers
         self.group_wgrad = os.environ.get("CLG_GROUP_WGRAD", "1") != "0"   # QKV + attention-output weight gradients in one launch
         self.dp = None                   # optional parallel.GradExchange
+        self.grads_zeroed = False        # the fused optimiser step left the gradient arena all zero
         self.L = cfgmod.num_encoder_layers(self.cfg)
         self.d = self.cfg.hidden_size
         self.H = self.d // 64
@@ -236,6 +237,7 @@ class Engine:
         self._anchor = torch.zeros(1, device=device, requires_grad=True)
         self._ws.clear()
         self.grads_consumed = True
+        self.grads_zeroed = False
         self._partials = torch.zeros(4096, dtype=torch.float32, device=device)
         from . import optim as _optim
         _optim.register_engine(self)
@@ -627,7 +629,8 @@ class Engine:
         first = self.slots[0].params[0]
         dropped = first.grad is None or first.grad.data_ptr() != self.grad_view(first).data_ptr()
         if dropped or self.grads_consumed:
-            self.g_flat.zero_()
+            if not self.grads_zeroed:
+                self.g_flat.zero_()
             for s in self.slots:
                 o = s.start
                 for p in s.params:
@@ -636,6 +639,7 @@ class Engine:
                         p.grad = self.g_flat[o:o + n].view(p.shape)
                     o += n
             self.grads_consumed = False
+        self.grads_zeroed = False       # this backward writes the arena
 
     def backward(self, dlogits, ticket):
         sv = self._saved

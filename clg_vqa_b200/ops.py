@@ -301,7 +301,7 @@ def sumsq(g_flat, partials, out, hot=None):
 
 
 def adamw_step(p_flat, g_flat, m_flat, v_flat, chunk_tensor, tensors_dev, *, sumsq=None, max_norm=1.0, gscale=1.0,
-               beta1=0.9, beta2=0.999, eps=1e-6, bias_c1=1.0, bias_c2=1.0, shadow=None, mask_bits=None, hot=None):
+               beta1=0.9, beta2=0.999, eps=1e-6, bias_c1=1.0, bias_c2=1.0, shadow=None, mask_bits=None, hot=None, zero_grad=False):
     _need_cuda(p_flat, g_flat, m_flat, v_flat, chunk_tensor, tensors_dev)
     p = L.AdamWParams()
     p.p, p.g, p.m, p.v = p_flat.data_ptr(), g_flat.data_ptr(), m_flat.data_ptr(), v_flat.data_ptr()
@@ -313,6 +313,7 @@ def adamw_step(p_flat, g_flat, m_flat, v_flat, chunk_tensor, tensors_dev, *, sum
     p.bias_c1, p.bias_c2 = float(bias_c1), float(bias_c2)
     p.shadow, p.mask_bits = _ptr(shadow), _ptr(mask_bits)
     p.hot = _ptr(hot)
+    p.zero_grad = int(bool(zero_grad))
     L.check(L.load().clg_adamw_step(C.byref(p), _stream()), "clg_adamw_step")
     _count()
 

@@ -16,6 +16,8 @@ from __future__ import annotations
 import math
 import weakref
 
+import os
+
 import torch
 from torch.optim import Optimizer
 from torch.optim.lr_scheduler import LambdaLR
@@ -44,6 +46,7 @@ def _engine_for(params):
     return eng
 
 
+_FUSED_ZERO = os.environ.get("CLG_FUSED_ZERO", "1") != "0"    # the fused step clears the gradients it consumes
 _PENDING_CLIP = {}   # id(engine) -> max_norm recorded by clip_grad_norm_ for the next fused step
 
 
@@ -162,8 +165,9 @@ class AdamW(Optimizer):
                        beta1=b1, beta2=b2, eps=g0["eps"], bias_c1=c1, bias_c2=c2,
                        shadow=eng.shadow if eng.precision == "bf16" else None,
                        mask_bits=eng.mask_bits if eng.has_masks else None,
-                       hot=eng._hot if eng._hot_valid else None)
+                       hot=eng._hot if eng._hot_valid else None, zero_grad=_FUSED_ZERO)
         eng._hot_valid = False
+        eng.grads_zeroed = _FUSED_ZERO        # the step cleared the arena as it read it: the next backward skips its fill
         for p in self.state:
             self.state[p]["step"] = t
         if eng.precision == "bf16":

@@ -334,7 +334,9 @@ typedef struct {
   float max_norm, gscale;
   float beta1, beta2, eps;
   float bias_c1, bias_c2;            /* 1-beta1^t, 1-beta2^t (1,1 when correct_bias is off) */
-  int32_t _pad;
+  int32_t zero_grad;                 /* 1: the step also leaves g == 0 everywhere (g is then written, despite the const):
+                                        the gradient it has just read is overwritten in place, which saves the separate
+                                        fill pass over the arena; blocks that `hot` marks all-zero are not touched */
   void* shadow; const uint32_t* mask_bits;
   const uint8_t* hot;                /* optional [n/256]: 0 = the block's g, m, v are all zero (marked by clg_sumsq on THIS
                                         gradient): only the decoupled decay p -= lr*wd*p is applied - bit-identical to the

@@ -273,3 +273,40 @@ def test_packed_rows_equal_padded_rows():
     # the masked text rows of the word-embedding gradient are exactly zero in both
     wg = gp["bert.embeddings.word_embeddings.weight"]
     assert torch.equal(torch.nonzero(wg.abs().sum(1) > 0).flatten().cpu(), torch.from_numpy(g["wordgrad_rows"]))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_step_clears_gradient_arena(precision):
+    """The fused AdamW overwrites each gradient with zero as it reads it (clgAdamWParams.zero_grad), so the next backward
+    skips its fill of the arena: after the step the arena is exactly zero, and a backward into the cleared arena gives the
+    gradients a backward after an explicit fill gives."""
+    from clg_vqa_b200 import optim
+    g, meta = _load_golden("uc2_L2_B4")
+    b = _batch(meta)
+    model, cfg, task_cfg = _build_uc2(meta, precision)
+    opt = optim.AdamW(optim.grouped_parameters(model, 4e-5, 1e-4), lr=4e-5)
+    eng = model.engine
+
+    def backward():
+        loss, _ = TU.ForwardModelsTrain(cfg, task_cfg, DEV, "TASK15", S.batch_tuple(b), model)
+        loss.backward()
+        return float(loss)
+
+    backward()
+    assert int(torch.count_nonzero(eng.g_flat)) > 0
+    optim.clip_grad_norm_(model.parameters(), 1.0)
+    opt.step()
+    assert eng.grads_zeroed and int(torch.count_nonzero(eng.g_flat)) == 0
+    model.zero_grad()
+    l1 = backward()                                   # into the arena the step cleared
+    assert not eng.grads_zeroed
+    g1 = eng.g_flat.clone()
+    eng.grads_consumed, eng.grads_zeroed = True, False
+    eng.g_flat.fill_(float("nan"))                    # an explicit fill must happen now
+    l2 = backward()
+    g2 = eng.g_flat
+    assert l1 == l2 and bool(torch.isfinite(g2).all())
+    assert float((g1 - g2).abs().max()) <= 1e-5 * float(g2.abs().max())      # split-K atomics: order noise only
+    # a step without a preceding clip (no hot-block map) clears everything as well
+    opt.step()
+    assert int(torch.count_nonzero(eng.g_flat)) == 0

@@ -108,7 +108,7 @@ def test_adamw_cold_blocks_bit_identical_to_dense():
     chunk_tensor = chunk_tensor.to(DEV)
     tens = torch.frombuffer(bytearray(bytes(metas)), dtype=torch.uint8).to(DEV)
     state = {}
-    for mode in ("dense", "hot"):
+    for mode in ("dense", "hot", "hot+zero", "dense+zero"):
         p = p0.clone(); m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV)
         shadow = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
         hot = torch.zeros(n // 256, device=DEV, dtype=torch.uint8)
@@ -121,12 +121,18 @@ def test_adamw_cold_blocks_bit_identical_to_dense():
             touched[ids] = True
             g.view(-1)[:k].view(rows, dim)[ids.to(DEV)] = torch.randn(150, dim, generator=gen).to(DEV)
             ss.zero_()
-            ops.sumsq(g, partials, ss, hot=hot if mode == "hot" else None)
+            g[n - 2 * L.CHUNK + 5] = 3.0                  # a chunk without an optimiser entry (chunk_tensor == -1)
+            use_hot = mode.startswith("hot")
+            ops.sumsq(g[:n - 2 * L.CHUNK], partials, ss, hot=hot if use_hot else None)
             ops.adamw_step(p, g, m, v, chunk_tensor, tens, sumsq=ss, max_norm=1.0, eps=1e-6, bias_c1=1 - 0.9 ** step,
-                           bias_c2=1 - 0.999 ** step, shadow=shadow, hot=hot if mode == "hot" else None)
+                           bias_c2=1 - 0.999 ** step, shadow=shadow, hot=hot if use_hot else None,
+                           zero_grad=mode.endswith("zero"))
+            # zero_grad: the step leaves the whole gradient arena cleared (also where no optimiser entry exists)
+            assert (int(torch.count_nonzero(g)) == 0) == mode.endswith("zero")
         state[mode] = (p, m, v, shadow, hot, touched)
-    for a, b in zip(state["dense"][:4], state["hot"][:4]):
-        assert torch.equal(a, b)
+    for other in ("hot", "hot+zero", "dense+zero"):
+        for a, b in zip(state["dense"][:4], state[other][:4]):
+            assert torch.equal(a, b)
     hot, touched = state["hot"][4], state["hot"][5]
     assert torch.equal(hot[:k // 256].view(rows, 3).bool().cpu(), touched[:, None].expand(rows, 3))
     assert int(hot[k // 256:].sum()) == 0
