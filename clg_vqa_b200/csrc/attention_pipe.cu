@@ -443,7 +443,6 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const int row = wq * 32 + lane;
     const int tg = (warp - 2 - 4 * g) * 32 + lane;
     const bool in_tile = row < NP;
-    const bool warp_live = wq * 32 < NP;
     float* kb = kbuf + g * 128;
     const uint32_t sP = sG0 + (uint32_t)g * 4u * TN, sdS = sP + 2 * TN;
     uint8_t* gP = gen + (sP - base);
@@ -456,27 +455,33 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       const int b = ((int)blockIdx.x + it * (int)gridDim.x) / H;
       if (a.cu) { row0 = __ldg(a.cu + b); Sb = __ldg(a.cu + b + 1) - row0; } else { row0 = b * S; Sb = S; }
     };
-    float kb_next = -INFINITY, lse_next = 0.f;
-    auto load_next = [&](int it) {
-      kb_next = -INFINITY; lse_next = 0.f;
+    // the row range is fetched two items ahead and the key bias / log-sum-exp one item ahead, so that neither of the two
+    // dependent L2 round trips is waited for where it is issued
+    int row0_c = 0, Sb_c = 0, row0_n = 0, Sb_n = 0;
+    float kb_c = -INFINITY, lse_c = 0.f;
+    auto load_vals = [&](int it, int r0, int sb) {
+      kb_c = -INFINITY; lse_c = 0.f;
       if (it >= n_it) return;
       const int w = (int)blockIdx.x + it * (int)gridDim.x;
-      int r0, sb;
-      item_rows(it, r0, sb);
-      if (tg < sb) kb_next = __ldg(a.key_bias + (int64_t)r0 + tg) * LOG2E;
-      if (row < sb) lse_next = __ldg(a.lse + ((int64_t)w) * S + row);      // w = b * H + h
+      if (tg < sb) kb_c = __ldg(a.key_bias + (int64_t)r0 + tg) * LOG2E;
+      if (row < sb) lse_c = __ldg(a.lse + ((int64_t)w) * S + row);      // w = b * H + h
     };
-    load_next(g);
+    if (g < n_it) item_rows(g, row0_c, Sb_c);
+    load_vals(g, row0_c, Sb_c);
+    if (g + 2 < n_it) item_rows(g + 2, row0_n, Sb_n);
     for (int it = g; it < n_it; it += 2) {
       const int u = it >> 1;
       const int s = it % NST;
       const int w = (int)blockIdx.x + it * (int)gridDim.x;
       const int b = w / H, h = w % H;
-      int row0, Sb;
-      item_rows(it, row0, Sb);
+      const int row0 = row0_c, Sb = Sb_c;
       const bool valid = row < Sb;
-      const float kbv = kb_next, lse_i = lse_next;
-      load_next(it + 2);                           // in flight during this item
+      const bool warp_live = wq * 32 < Sb;         // this warp's 32 rows hold a query of the item
+      const int cl = min(NP, (Sb + 15) & ~15);     // key columns [cl, 128) hold no key of the item: exact zeros
+      const float kbv = kb_c, lse_i = lse_c;
+      load_vals(it + 2, row0_n, Sb_n);             // in flight during this item
+      row0_c = row0_n; Sb_c = Sb_n;
+      if (it + 4 < n_it) item_rows(it + 4, row0_n, Sb_n);
       if (tg == 0) bulk_wait_read<0>();            // the previous dQ/dK/dV stores have read the staging tiles
       named_bar(1 + g, 128);
       if (tg < 128) kb[tg] = kbv;
@@ -508,7 +513,7 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         // >= S (kb = -inf) and for query rows >= S (lse2 = +inf), so no per-element predicates are needed
         const float lse2 = valid ? lse_i * LOG2E : INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < NP; c += 16) {
+        for (int c = 0; c < cl; c += 16) {
           float sv[16], dv[16];
           tmem_ld16_nowait(tbase + c, sv);
           tmem_ld16_nowait(tbase + 128 + c, dv);
@@ -550,10 +555,16 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           }
         }
         if (in_tile) {
-          for (int c = NP; c < 128; c += 8) {          // unused key columns are read as M rows of the transposed MMAs
+          for (int c = cl; c < 128; c += 8) {          // unused key columns are read as M rows of the transposed MMAs
             *reinterpret_cast<uint4*>(gP + (c >> 6) * TN + psw_off(row, c & 63)) = make_uint4(0, 0, 0, 0);
             *reinterpret_cast<uint4*>(gdS + (c >> 6) * TN + psw_off(row, c & 63)) = make_uint4(0, 0, 0, 0);
           }
+        }
+      } else if (in_tile) {
+        // rows past the item's last query (in the packed layout they belong to the next item): P = dS = 0
+        for (int c = 0; c < 128; c += 8) {
+          *reinterpret_cast<uint4*>(gP + (c >> 6) * TN + psw_off(row, c & 63)) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(gdS + (c >> 6) * TN + psw_off(row, c & 63)) = make_uint4(0, 0, 0, 0);
         }
       }
       fence_proxy_async();

@@ -25,3 +25,14 @@ for backend, name in ((2, "one CTA / head"), (0, "pipelined")):
     tf = timeit(lambda: ops.attention_fwd(qkv, kb, ctx, lse, B, S, H, 0.125, site))
     tb = timeit(lambda: ops.attention_bwd(qkv, kb, ctx, dctx, lse, dqkv, B, S, H, 0.125, site))
     print("%-16s fwd %7.1f us   bwd %7.1f us" % (name, tf, tb))
+# packed rows (engine._forward with CLG_PACK): item b owns rows cu[b] .. cu[b+1], lengths like the synthetic GQA batch
+g = torch.Generator(device="cpu").manual_seed(0)
+lens = torch.randint(int(os.environ.get("SMIN", 44)), S + 1, (B,), generator=g)
+cu = torch.zeros(B + 1, dtype=torch.int32); cu[1:] = torch.cumsum(lens, 0)
+Mp = int(cu[-1]); cu = cu.to(dev)
+qkv_p = qkv[:Mp].contiguous(); kb_p = torch.zeros(Mp, device=dev); ctx_p = torch.zeros(Mp, D, device=dev, dtype=torch.bfloat16)
+dctx_p = dctx[:Mp].contiguous(); dqkv_p = torch.zeros_like(qkv_p)
+ops.set_attention_backend(0)
+tf = timeit(lambda: ops.attention_fwd(qkv_p, kb_p, ctx_p, lse, B, S, H, 0.125, site, cu_rows=cu, total_rows=Mp))
+tb = timeit(lambda: ops.attention_bwd(qkv_p, kb_p, ctx_p, dctx_p, lse, dqkv_p, B, S, H, 0.125, site, cu_rows=cu, total_rows=Mp))
+print("%-16s fwd %7.1f us   bwd %7.1f us   (%d packed rows, mean length %.1f)" % ("pipelined packed", tf, tb, Mp, Mp / B))
