@@ -96,11 +96,40 @@ smallk_fwd_kernel(const TA* __restrict__ A, const TB* __restrict__ B, int M, int
     As[r][k] = (r0 + r < M && k < K) ? to_f32<TA>(A[(int64_t)(r0 + r) * lda + k]) : 0.f;
   }
   __syncthreads();
+  const int rows = min(SK_ROWS, M - r0);
+  // plain form (bias only, fp32 rows of whole float4s): four columns per thread, 16 B stores
+  const bool plain = e.act == CLG_ACT_NONE && !e.drop.on && !e.residual && !e.mask_bits && !e.colsum && !e.accumulate &&
+                     e.alpha == 1.f && e.c_dtype == CLG_F32 && (N & 3) == 0 && (e.ldc & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(e.C) & 15) == 0;
+  if (plain) {
+    for (int n = threadIdx.x * 4; n < N; n += 1024) {
+      float w[4][SK_MAX], bv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bv[j] = e.bias ? __ldg(e.bias + n + j) : 0.f;
+#pragma unroll
+        for (int k = 0; k < SK_MAX; ++k) w[j][k] = k < K ? to_f32<TB>(B[(int64_t)(n + j) * ldb + k]) : 0.f;
+      }
+      for (int r = 0; r < rows; ++r) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < SK_MAX; ++k) {
+          if (k < K) {
+            const float a = As[r][k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fmaf(a, w[j][k], acc[j]);
+          }
+        }
+        *reinterpret_cast<float4*>((float*)e.C + (int64_t)(r0 + r) * e.ldc + n) =
+            make_float4(acc[0] + bv[0], acc[1] + bv[1], acc[2] + bv[2], acc[3] + bv[3]);
+      }
+    }
+    return;
+  }
   for (int n = threadIdx.x; n < N; n += 256) {
     float w[SK_MAX];
 #pragma unroll
     for (int k = 0; k < SK_MAX; ++k) w[k] = k < K ? to_f32<TB>(B[(int64_t)n * ldb + k]) : 0.f;
-    const int rows = min(SK_ROWS, M - r0);
     for (int r = 0; r < rows; ++r) {
       float acc = 0.f;
 #pragma unroll
