@@ -145,6 +145,15 @@ class AsyncCheckpointer:
             return [rebuild(t) for t in host_now]
         return finish
 
+    def prepare(self, model, optimizer=None):
+        """Allocate the snapshot and pinned host buffers now (a few seconds for 3.4 GB) instead of inside the first
+        `save` of the run.  The optimiser's moment arenas exist after its first step; call again then, or leave
+        them to the first save."""
+        m = model.module if hasattr(model, "module") else model
+        for f in _flats(m, optimizer):
+            if f is not None and f.is_cuda:
+                self._arena_for(f)
+
     # -- writer --------------------------------------------------------------------------------------
     def submit(self, trees: List[Any], flats: List[torch.Tensor], write: Callable[[List[Any]], None]):
         self.wait()                                   # one set of snapshot buffers
@@ -184,6 +193,11 @@ def _clone_host_leaves(x):
 
 
 _DEFAULT = AsyncCheckpointer()
+
+
+def prepare(model, optimizer=None):
+    """Pre-allocate the default checkpointer's buffers (see AsyncCheckpointer.prepare)."""
+    _DEFAULT.prepare(model, optimizer)
 
 
 def wait():

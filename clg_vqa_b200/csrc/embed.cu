@@ -70,6 +70,67 @@ embed_text_bwd_kernel(const clgEmbedTextBwdParams p) {
   }
 }
 
+// N = 32 * NR (768): a warp walks EMB_BPW samples at one token index t, keeps the row in registers and
+//  - skips rows that are entirely zero (adding them changes nothing; the masked text positions - 40 % of a GQA batch -
+//    all carry the padding position id and used to queue thousands of atomic adds of 0.0 on that one row);
+//  - accumulates the position-table contribution in registers while the position id stays the same (at a given t it is
+//    the same for every unpadded sample) and flushes it with one atomic per column: 8x fewer atomics on the ~40 hot rows.
+static constexpr int EMB_BPW = 8;
+template <int NR>
+__global__ void __launch_bounds__(EMB_WARPS * 32)
+embed_text_bwd_rows_kernel(const clgEmbedTextBwdParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int N = 32 * NR;
+  const int t = blockIdx.x % p.T;
+  const int b0 = ((int)(blockIdx.x / p.T) * EMB_WARPS + warp) * EMB_BPW;
+  float acc[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) acc[i] = 0.f;
+  int acc_pos = -1;
+  auto flush = [&]() {
+    if (acc_pos >= 0 && p.dpos) {
+      float* dp = p.dpos + (int64_t)acc_pos * N;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) { atomicAdd(dp + lane + 32 * i, acc[i]); acc[i] = 0.f; }
+    }
+    acc_pos = -1;
+  };
+  for (int b = b0; b < min(p.B, b0 + EMB_BPW); ++b) {
+    const int64_t tok = (int64_t)b * p.T + t;
+    const float* g = p.dout + map_row(p.dout_map, tok) * p.ld_dout;
+    float v[NR];
+    bool nz = false;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) { v[i] = g[lane + 32 * i]; nz |= v[i] != 0.f; }
+    if (!__any_sync(0xffffffffu, nz)) continue;
+    const int64_t id = p.ids[tok];
+    int pos;
+    if (p.pos_mode == 0) pos = text_pos_id(p.ids + (int64_t)b * p.T, t, p.T, p.pad_id, lane);
+    else pos = p.pos_base + t;
+    if (pos != acc_pos) { flush(); acc_pos = pos; }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) acc[i] += v[i];
+    if (p.dword && id != p.pad_id) {                 // padding_idx row gets no gradient
+      float* dw = p.dword + id * N;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) atomicAdd(dw + lane + 32 * i, v[i]);
+    }
+    if (p.dtype_tab && p.seg) {
+      const int64_t sg = p.seg[tok];
+      if (!p.type_row0_has_total) {
+        float* dt = p.dtype_tab + sg * N;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) atomicAdd(dt + lane + 32 * i, v[i]);
+      } else if (sg != 0) {                          // row 0 was pre-loaded with the all-token total: move this row out
+        float* dt = p.dtype_tab + sg * N;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) { atomicAdd(dt + lane + 32 * i, v[i]); atomicAdd(p.dtype_tab + lane + 32 * i, -v[i]); }
+      }
+    }
+  }
+  flush();
+}
+
 // Deterministic row reduction for the data-parallel word-embedding gradient.  Input: the all-gathered (token id,
 // gradient row) list sorted by id (stable).  One CTA per list position; the CTA at the head of a run of equal ids sums
 // that run's rows in list order (the warps split the columns) and adds the result to the table row.  Every rank runs it
@@ -143,6 +204,11 @@ extern "C" int clg_embed_text_bwd(const clgEmbedTextBwdParams* p, clgStream_t st
   int st = require_sm100();
   if (st != CLG_OK) return st;
   const int64_t toks = (int64_t)p->B * p->T;
+  if (p->N == 768) {
+    const int bgroups = (p->B + EMB_WARPS * EMB_BPW - 1) / (EMB_WARPS * EMB_BPW);
+    embed_text_bwd_rows_kernel<24><<<(unsigned)(bgroups * p->T), EMB_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(*p);
+    return check_launch("embed_text_bwd_rows_kernel");
+  }
   embed_text_bwd_kernel<<<(unsigned)ceil_div64(toks, EMB_WARPS), EMB_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(*p);
   return check_launch("embed_text_bwd_kernel");
 }
