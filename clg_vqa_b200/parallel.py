@@ -7,7 +7,7 @@ stream after backward, scales by 1/world and copies back.
 
 Here
   * gradients already live in one flat arena (engine.g_flat) - no flatten / unflatten copies;
-  * the dense part is all-reduced IN PLACE in per-layer buckets that are launched as soon as the layer's
+  * the dense part is all-reduced IN PLACE in buckets of four layers that are launched as soon as the last layer's
     backward has been enqueued, so NCCL overlaps the rest of the backward;
   * the 192 M-parameter word-embedding gradient is row-sparse (<= B*40 rows): ranks all-gather the
     per-token gradient rows + token ids (31 MB per rank at B=256) instead of all-reducing 768 MB, and every rank
@@ -20,6 +20,7 @@ The class only needs `torch.distributed` collectives, so its logic is exercised 
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
@@ -35,6 +36,7 @@ class GradExchange:
         self.done_ranges: List[Tuple[int, int]] = []
         self.row_ids: List[torch.Tensor] = []      # word-gradient rows of the micro-steps since the last exchange
         self.row_vals: List[torch.Tensor] = []
+        self.bucket_layers = int(os.environ.get("CLG_DP_BUCKET_LAYERS", "4"))
 
     # -- generic pieces (device-agnostic; tested with gloo) ---------------------------------------
     def reduce_range(self, flat: torch.Tensor, start: int, end: int):
@@ -109,10 +111,19 @@ class GradExchange:
         return s0.start, s1.start + _pad(s1.numel)
 
     def layer_done(self, engine, layer: int):
+        """backward of encoder layer `layer` is enqueued (layers finish in descending order): all-reduce the finished
+        layers in buckets of CLG_DP_BUCKET_LAYERS (default 4: measured 13.5 vs 13.8 ms per step at N = 2 and 13.9 vs 14.0 at
+        N = 4 against per-layer buckets - fewer NCCL kernels taking SMs from the persistent GEMM grids; 0 = one exchange
+        after the backward, no overlap: 13.6 at N = 2)"""
         if not self.enabled or self.world == 1:
             return
-        a, b = self._layer_range(engine, layer)
-        self.reduce_range(engine.g_flat, a, b)
+        k = self.bucket_layers
+        if k <= 0:
+            return
+        if layer % k == 0:
+            a, _ = self._layer_range(engine, layer)
+            _, b = self._layer_range(engine, min(layer + k, engine.L) - 1)
+            self.reduce_range(engine.g_flat, a, b)
 
     def after_backward(self, engine):
         """everything that was not sent per layer, except the word-embedding table, which is exchanged
