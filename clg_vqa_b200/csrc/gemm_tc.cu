@@ -22,7 +22,14 @@ static constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
 static constexpr int UMMA_K = 16;
 // warps: TMA producer, MMA issuer, then the epilogue warps (8; 12 for the ALU-heavy GeLU-pair epilogue, whose per-tile
 // work must fit under a K = 768 main loop)
-template <int EPI> __host__ __device__ constexpr int epi_warps() { return EPI == EPI_GELU_PAIR ? 12 : 8; }
+// epilogue warps per CTA (multiples of 4: one set per TMEM lane quarter); the math-heavy forms get more
+#ifndef CLG_GELU_EPI_WARPS
+#define CLG_GELU_EPI_WARPS 12
+#endif
+#ifndef CLG_MULAUX_EPI_WARPS
+#define CLG_MULAUX_EPI_WARPS 8
+#endif
+template <int EPI> __host__ __device__ constexpr int epi_warps() { return EPI == EPI_GELU_PAIR ? CLG_GELU_EPI_WARPS : (EPI == EPI_MUL_AUX ? CLG_MULAUX_EPI_WARPS : 8); }
 template <int EPI> __host__ __device__ constexpr int num_threads() { return 64 + 32 * epi_warps<EPI>(); }
 static constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KiB
 
