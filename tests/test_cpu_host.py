@@ -158,3 +158,45 @@ def test_from_pretrained_roundtrip(tmp_path):
     assert "cls.predictions.bias" in info["unexpected_keys"] and not info["missing_keys"]
     for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
         assert k1 == k2 and torch.equal(v1, v2)
+
+
+def test_dp_bucket_ranges_cover_every_layer_once(monkeypatch):
+    """parallel.GradExchange.layer_done: the layers finish in descending order and are all-reduced in buckets of
+    CLG_DP_BUCKET_LAYERS; whatever the bucket size, the launched ranges tile the layers' arena range exactly once and
+    after_backward sends the rest (everything but the word table, which travels as rows)."""
+    import types
+    import torch
+    from clg_vqa_b200 import parallel
+    from clg_vqa_b200.engine import _pad
+
+    L, per = 12, 8
+    sizes = [1000, 10, 70, 10] + [5000 + 37 * i for i in range(L * per)] + [123456, 900, 40]     # ..., word table, two more
+    slots, o = [], 0
+    for i, n in enumerate(sizes):
+        slots.append(types.SimpleNamespace(start=o, numel=n, index=i))
+        o += _pad(n)
+    word = torch.nn.Parameter(torch.zeros(1))
+    wslot = slots[4 + L * per]
+    eng = types.SimpleNamespace(slots=slots, L=L, total=o, g_flat=torch.zeros(1), word_table_param=lambda: word,
+                                _slot_of_param={id(word): wslot}, reduce_word_rows=None, prereduce_word_rows=None)
+    lo, hi = slots[4].start, slots[4 + L * per - 1].start + _pad(slots[4 + L * per - 1].numel)
+    for k in (1, 2, 4, 5, 12, 0):
+        ex = parallel.GradExchange(world_size=2)
+        ex.bucket_layers = k
+        sent = []
+        monkeypatch.setattr(ex, "reduce_range", lambda flat, a, b, sent=sent, ex=ex: (sent.append((a, b)), ex.done_ranges.append((a, b))))
+        monkeypatch.setattr(ex, "exchange_rows_deterministic", lambda *a, **kw: None)
+        for layer in range(L - 1, -1, -1):
+            ex.layer_done(eng, layer)
+        during = sorted(sent)
+        if k > 0:
+            assert during[0][0] == lo and during[-1][1] == hi
+            assert all(during[i][1] == during[i + 1][0] for i in range(len(during) - 1))          # no gap, no overlap
+            assert len(during) == -(-L // k)
+        else:
+            assert during == []
+        ex.after_backward(eng)
+        cover = sorted(sent)
+        assert cover[0][0] == 0 and cover[-1][1] == o
+        gaps = [(cover[i][1], cover[i + 1][0]) for i in range(len(cover) - 1) if cover[i][1] != cover[i + 1][0]]
+        assert gaps == [(wslot.start, wslot.start + _pad(wslot.numel))]                           # only the word table is skipped
