@@ -249,6 +249,9 @@ def _save_impl(path, logger, epoch_id, model, optimizer, scheduler, global_step,
     trees = [model_to_save.state_dict(), optimizer.state_dict()]
     meta = {"scheduler_state_dict": scheduler.state_dict() if scheduler is not None else None, "global_step": global_step,
             "epoch_id": epoch_id, "tb_logger": tb_logger, "score": score}
+    eng = model_to_save.__dict__.get("_engine")
+    if eng is not None:       # extra key (ignored by the reference's resume): the dropout stream continues after a resume
+        meta["clg_engine_rng"] = eng.rng_state()
 
     def write(host_trees):
         sd, osd = host_trees
@@ -299,5 +302,9 @@ def resume(path, model, optimizer, scheduler, tb_logger):
         start_epoch = int(checkpoint["epoch_id"]) + 1
         tb_logger = checkpoint["tb_logger"]
         best_score = checkpoint.get("score", float("-inf"))
+        rng = checkpoint.get("clg_engine_rng")
+        target = model.module if hasattr(model, "module") else model
+        if rng is not None and hasattr(target, "engine"):
+            target.engine.set_rng_state(rng)
         del checkpoint
     return start_iter_id, global_step, start_epoch, tb_logger, best_score

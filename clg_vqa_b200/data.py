@@ -69,7 +69,12 @@ class DevicePrefetcher:
             self.stream = torch.cuda.Stream(device=self.device)
             self.slots = [None, None]
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
-        self.free = [None, None]
+        # Both slots may still be read by kernels already enqueued on the consumer's stream (the last batches of the
+        # adopted prefetcher; a freshly allocated slot is ordered on the allocating stream): the first copies into them
+        # wait for everything the consumer has enqueued so far.
+        seed = torch.cuda.Event()
+        seed.record(torch.cuda.current_stream(self.device))
+        self.free = [seed, seed]
         self.k = 0                 # index of the next batch to be yielded
         self.loaded = -1           # index of the last batch whose copy has been issued
         self.exhausted = False

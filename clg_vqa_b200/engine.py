@@ -84,12 +84,17 @@ class Engine:
         self._shadow_versions = None
         self._mask_versions = None
         self._struct_sig = None
-        self.base_seed = 0x5EED
+        # dropout stream: keyed on torch's seed (torch.manual_seed / args.seed picks the stream, train_task.py:L189-191),
+        # the rank (parallel.attach folds it in: independent masks per process, as with per-process RNGs) and the step
+        # counter (saved / restored by checkpoint.save / resume)
+        self.base_seed = (int(torch.initial_seed()) ^ 0x5EED) & 0x7FFFFFFFFFFFFFFF
         self.step_counter = 0
         self.grads_consumed = True       # True: next backward zeroes the gradient arena first
         self.pack_enabled = os.environ.get("CLG_PACK", "1") != "0"   # drop masked positions before the encoder layers
         self.group_wgrad = os.environ.get("CLG_GROUP_WGRAD", "1") != "0"   # QKV + attention-output weight gradients in one launch
         self.dp = None                   # optional parallel.GradExchange
+        self.grad_scale = 1.0            # 1/world under data parallelism (parallel.attach): the arena holds the SUM over ranks
+        self.probe = None                # parity-test hook: {"inject": {l: [B,S,d] fp32}, "capture": {}} (see _probe_*)
         self.grads_zeroed = False        # the fused optimiser step left the gradient arena all zero
         self.L = cfgmod.num_encoder_layers(self.cfg)
         self.d = self.cfg.hidden_size
@@ -379,6 +384,12 @@ class Engine:
             self.metas_host[i].mask_off = s.mask_off if (s.mask_mods is not None and self.has_masks) else -1
         self.tensors_dev = torch.frombuffer(bytearray(bytes(self.metas_host)), dtype=torch.uint8).to(self.device)
 
+    def invalidate_masks(self):
+        """masks were rewritten behind torch's back (pruning.global_magnitude_prune): repack the mask bits and re-cast
+        the masked weight shadow at the next forward"""
+        self._mask_versions = None
+        self._shadow_versions = None
+
     def mark_shadow_fresh(self):
         """called by the fused optimiser after it rewrote parameters AND shadows in one kernel"""
         self._shadow_versions = tuple(p._version for s in self.slots if s.mask_mods is not None for p in s.params)
@@ -468,10 +479,63 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # dropout sites
     # ------------------------------------------------------------------------------------------
+    def step_seed(self) -> int:
+        return (self.base_seed * 0x9E3779B1 + self.step_counter) & 0x7FFFFFFFFFFFFFFF
+
+    def rng_state(self) -> dict:
+        return {"base_seed": int(self.base_seed), "step_counter": int(self.step_counter)}
+
+    def set_rng_state(self, st: dict):
+        self.base_seed = int(st["base_seed"])
+        self.step_counter = int(st["step_counter"])
+
     def _site(self, idx: int, p: float, training: bool) -> DropSite:
         if not training or p <= 0.0:
             return ops.NO_DROP
         return DropSite(p, self._seed, idx << 40)
+
+    # ------------------------------------------------------------------------------------------
+    # parity-test hook (tests/test_layerwise_gpu.py): teacher-forced per-layer comparison.  `probe["inject"][l]` replaces
+    # the input of encoder layer l (l = L: the input of the head) by a caller-supplied [B, S, d] fp32 hidden state (and
+    # its bf16 rounding as the GEMM operand); `probe["capture"]` receives the embedding output ("emb") and every layer's
+    # output as [B, S, d] fp32 (packed rows scattered back; dropped rows read 0).  Off (None) on the product path.
+    # ------------------------------------------------------------------------------------------
+    def _probe_inject(self, l, x, x_lp, B, S, pack):
+        inj = self.probe.get("inject", {}).get(l) if self.probe is not None else None
+        if inj is None:
+            return
+        v = inj.to(device=self.device, dtype=torch.float32).reshape(B * S, self.d)
+        n = B * S
+        if pack is not None:
+            n = pack[0]
+            v = v[pack[2][:n].long()]
+        x[:n].copy_(v)
+        if x_lp is not x:
+            x_lp[:n].copy_(v.to(x_lp.dtype))
+
+    def _probe_inject_grad(self, l, dx, B, S, pack):
+        """backward twin of _probe_inject: `probe["inject_grad"][l]` replaces d(loss)/d(hidden state l) ([B, S, d] fp32),
+        so that every layer's parameter gradients can be compared with the oracle's without the layers above it"""
+        inj = self.probe.get("inject_grad", {}).get(l) if self.probe is not None else None
+        if inj is None:
+            return
+        v = inj.to(device=self.device, dtype=torch.float32).reshape(B * S, self.d)
+        n = B * S
+        if pack is not None:
+            n = pack[0]
+            v = v[pack[2][:n].long()]
+        dx[:n].copy_(v)
+
+    def _probe_capture(self, key, x, B, S, pack):
+        if self.probe is None:
+            return
+        if pack is None:
+            out = x[:B * S].reshape(B, S, self.d).clone()
+        else:
+            out = torch.zeros(B * S, self.d, dtype=x.dtype, device=x.device)
+            out[pack[2][:pack[0]].long()] = x[:pack[0]]
+            out = out.view(B, S, self.d)
+        self.probe.setdefault("capture", {})[key] = out
 
     # ------------------------------------------------------------------------------------------
     # forward
@@ -508,7 +572,7 @@ class Engine:
         bf = lp == torch.bfloat16
         eps = float(cfg.layer_norm_eps)
         self.step_counter += 1
-        self._seed = (self.base_seed * 0x9E3779B1 + self.step_counter) & 0x7FFFFFFFFFFFFFFF
+        self._seed = self.step_seed()
         self._ticket += 1
         E = self.model.bert.embeddings
         p_h = float(cfg.hidden_dropout_prob)
@@ -543,6 +607,7 @@ class Engine:
                           out_map=rowmap(R, T, S), dropout=self._site(1, p_h, training))
         # ---- encoder layers
         x, x_lp, kb = ws["x0"], ws["x0_lp"], ws["kb"]
+        self._probe_capture("emb", x, B, S, None)
         # Packing: masked positions (text padding, missing regions) are dropped before the encoder.  Exact: their key
         # bias (-10000) makes exp() underflow to 0 for every kept query, nothing downstream reads their outputs (the
         # pooler takes token 0, which is always kept) and hence their gradients vanish identically.  The layers then run
@@ -563,10 +628,13 @@ class Engine:
         for l in range(Ln):
             sa, so, fi, fo = self.layer_mods[l]
             lw = ws["layers"][l % nslots]
+            self._probe_inject(l, x, x_lp, B, S, pack)
             x, x_lp = self._layer_fwd(lw, x, x_lp, kb, B, S, sa.query, so.dense, so.LayerNorm, fi.dense, fo.dense,
                                       fo.LayerNorm, eps, 0.125, self._site(2 + 4 * l, p_a, training),
                                       self._site(3 + 4 * l, p_h, training), self._site(4 + 4 * l, p_h, training), bf,
                                       rows=rows, cu=cu)
+            self._probe_capture(l, x, B, S, pack)
+        self._probe_inject(Ln, x, x_lp, B, S, pack)
         logits = self._head_fwd(ws, x_lp, B, S, task_id, self.pooler.dense, self.pool_act,
                                 self._site(2 + 4 * Ln, float(self.model.dropout.p), training), eps, bf, pack=pack)
         if save:
@@ -768,6 +836,7 @@ class Engine:
         rows = pack[0] if pack else None
         cu = pack[1] if pack else None
         kb = sv.get("kb", ws["kb"])
+        self._probe_inject_grad(Ln, ws["dx"], B, S, pack)
         for l in reversed(range(Ln)):
             sa, so, fi, fo = self.layer_mods[l]
             lw = ws["layers"][l]
@@ -778,6 +847,7 @@ class Engine:
             self._layer_bwd(ws, lw, x_in, x_in_lp, kb, B, S, sa.query, so.dense, so.LayerNorm, fi.dense, fo.dense,
                             fo.LayerNorm, 0.125, self._site(2 + 4 * l, p_a, training), self._site(3 + 4 * l, p_h, training),
                             self._site(4 + 4 * l, p_h, training), rows=rows, cu=cu)
+            self._probe_inject_grad(l, ws["dx"], B, S, pack)
             if self.dp is not None:
                 self.dp.layer_done(self, l)
         dx = ws["dx"]

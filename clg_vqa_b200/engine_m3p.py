@@ -48,7 +48,7 @@ def forward(eng, ids, feats, locs, task_id, seg, tmask, imask, training, save):
     bf = lp == torch.bfloat16
     eps = 1e-12
     eng.step_counter += 1
-    eng._seed = (eng.base_seed * 0x9E3779B1 + eng.step_counter) & 0x7FFFFFFFFFFFFFFF
+    eng._seed = eng.step_seed()
     eng._ticket += 1
     p_h, p_a = _p(cfg)
     IE = enc.image_embeddings
@@ -82,14 +82,18 @@ def forward(eng, ids, feats, locs, task_id, seg, tmask, imask, training, save):
                       mean=ws["m_e"], rstd=ws["r_e"], row_valid=ws["row_valid"], valid_pre=True,
                       dropout=eng._site(0, p_h, training))
     x, x_lp = ws["x0"], ws["x0_lp"]
+    eng._probe_capture("emb", x, B, S, None)
     nslots = len(ws["layers"])
     for l in range(Ln):
         a = enc.attentions[l]
         lw = ws["layers"][l % nslots]
+        eng._probe_inject(l, x, x_lp, B, S, None)
         x, x_lp = eng._layer_fwd(lw, x, x_lp, ws["kb"], B, S, a.q_lin, a.out_lin, enc.layer_norm1[l], enc.ffns[l].lin1,
                                  enc.ffns[l].lin2, enc.layer_norm2[l], eps, 0.125, eng._site(2 + 4 * l, p_a, training),
                                  eng._site(3 + 4 * l, p_h, training), eng._site(4 + 4 * l, p_h, training), bf,
                                  row_valid=ws["row_valid"])
+        eng._probe_capture(l, x, B, S, None)
+    eng._probe_inject(Ln, x, x_lp, B, S, None)
     logits = eng._head_fwd(ws, x_lp, B, S, task_id, eng.pooler.dense, eng.pool_act,
                            eng._site(2 + 4 * Ln, float(eng.model.dropout.p), training),
                            float(getattr(cfg, "layer_norm_eps", 1e-12)), bf)
@@ -111,6 +115,7 @@ def backward(eng, dl, sv):
     x_last_lp = last["x2_lp"] if last is not None else ws["x0_lp"]
     eng._head_bwd(ws, sv, dl, x_last_lp, eng.pooler.dense, ops.ACT_DTANH,
                   eng._site(2 + 4 * Ln, float(eng.model.dropout.p), training))
+    eng._probe_inject_grad(Ln, ws["dx"], B, S, None)
     for l in reversed(range(Ln)):
         a = enc.attentions[l]
         lw = ws["layers"][l]
@@ -121,6 +126,7 @@ def backward(eng, dl, sv):
         eng._layer_bwd(ws, lw, x_in, x_in_lp, ws["kb"], B, S, a.q_lin, a.out_lin, enc.layer_norm1[l], enc.ffns[l].lin1,
                        enc.ffns[l].lin2, enc.layer_norm2[l], 0.125, eng._site(2 + 4 * l, p_a, training),
                        eng._site(3 + 4 * l, p_h, training), eng._site(4 + 4 * l, p_h, training), row_valid=ws["row_valid"])
+        eng._probe_inject_grad(l, ws["dx"], B, S, None)
         if eng.dp is not None:
             eng.dp.layer_done(eng, l)
     dx = ws["dx"]

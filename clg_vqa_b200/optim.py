@@ -46,6 +46,7 @@ def _engine_for(params):
     return eng
 
 
+_OPTIMIZERS = weakref.WeakSet()      # live AdamW instances (clip_grad_norm_'s torch fallback tells them it pre-scaled)
 _FUSED_ZERO = os.environ.get("CLG_FUSED_ZERO", "1") != "0"    # the fused step clears the gradients it consumes
 _PENDING_CLIP = {}   # id(engine) -> max_norm recorded by clip_grad_norm_ for the next fused step
 
@@ -57,6 +58,12 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0):
     params = [p for p in (parameters if not isinstance(parameters, torch.Tensor) else [parameters])]
     eng = _engine_for(params)
     if eng is None or float(norm_type) != 2.0:
+        scale = float(getattr(eng, "grad_scale", 1.0)) if eng is not None else 1.0
+        if scale != 1.0:        # data parallel: the arena holds the SUM over ranks; clip the average, like the reference
+            eng.g_flat.mul_(scale)
+            for o in list(_OPTIMIZERS):
+                if getattr(o, "grad_scale", 1.0) != 1.0 and _engine_for([p for g in o.param_groups for p in g["params"]]) is eng:
+                    o._grads_prescaled = True
         return torch.nn.utils.clip_grad_norm_(params, max_norm, norm_type)
     eng._sumsq.zero_()
     # the norm pass also marks which 256-element blocks of the gradient arena hold a non-zero (eng._hot); the fused
@@ -64,7 +71,8 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0):
     ops.sumsq(eng.g_flat, eng._partials, eng._sumsq, hot=eng._hot)
     eng._hot_valid = True
     _PENDING_CLIP[id(eng)] = float(max_norm)
-    return eng._sumsq.sqrt()
+    # the norm of the AVERAGED gradient (what the reference logs and clips after apex's 1/world)
+    return eng._sumsq.sqrt() * float(getattr(eng, "grad_scale", 1.0))
 
 
 class AdamW(Optimizer):
@@ -81,6 +89,8 @@ class AdamW(Optimizer):
         super().__init__(params, defaults)
         self._fused = None
         self.grad_scale = 1.0          # e.g. 1/world_size when gradients were summed across ranks
+        self._grads_prescaled = False  # the torch clip fallback already multiplied the arena by grad_scale
+        _OPTIMIZERS.add(self)
 
     # -- fused path ------------------------------------------------------------------------------
     def _fused_state(self):
@@ -159,9 +169,15 @@ class AdamW(Optimizer):
         c1 = 1.0 - b1 ** t if g0["correct_bias"] else 1.0
         c2 = 1.0 - b2 ** t if g0["correct_bias"] else 1.0
         max_norm = _PENDING_CLIP.pop(id(eng), None)
+        gscale = 1.0 if self._grads_prescaled else self.grad_scale
+        self._grads_prescaled = False
+        if not eng._hot_valid:
+            # no norm pass marked the blocks of THIS gradient: the update is dense, and it makes m / v non-zero wherever the
+            # gradient is - keep every block hot from here on, or a later clipped step would skip their moment decay
+            eng._hot.fill_(1)
         ops.adamw_step(eng.p_flat, eng.g_flat, fs["m"], fs["v"], fs["chunk_tensor"], tens,
                        sumsq=eng._sumsq if max_norm is not None else None,
-                       max_norm=max_norm if max_norm is not None else 0.0, gscale=self.grad_scale,
+                       max_norm=max_norm if max_norm is not None else 0.0, gscale=gscale,
                        beta1=b1, beta2=b2, eps=g0["eps"], bias_c1=c1, bias_c2=c2,
                        shadow=eng.shadow if eng.precision == "bf16" else None,
                        mask_bits=eng.mask_bits if eng.has_masks else None,
@@ -190,11 +206,18 @@ class AdamW(Optimizer):
     # -- reference (per-parameter) path ------------------------------------------------------------
     @torch.no_grad()
     def _step_unfused(self):
+        gscale = 1.0 if self._grads_prescaled else float(self.grad_scale)
+        self._grads_prescaled = False
+        eng = _engine_for([p for g in self.param_groups for p in g["params"]])
+        clip = _PENDING_CLIP.pop(id(eng), None) if eng is not None else None
+        if clip is not None:      # a fused-path clip_grad_norm_ recorded the norm but this step cannot run fused
+            total = float(eng._sumsq.sqrt()) * gscale
+            gscale = gscale * min(1.0, clip / (total + 1e-6))
         for group in self.param_groups:
             for p in group["params"]:
                 if p.grad is None:
                     continue
-                grad = p.grad
+                grad = p.grad if gscale == 1.0 else p.grad * gscale
                 state = self.state[p]
                 if len(state) == 0:
                     state["step"] = 0

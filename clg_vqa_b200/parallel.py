@@ -37,6 +37,7 @@ class GradExchange:
         self.row_ids: List[torch.Tensor] = []      # word-gradient rows of the micro-steps since the last exchange
         self.row_vals: List[torch.Tensor] = []
         self.bucket_layers = int(os.environ.get("CLG_DP_BUCKET_LAYERS", "4"))
+        self.scale_after_exchange = 1.0   # 1/world when the optimiser cannot fold the average into its gradient read
 
     # -- generic pieces (device-agnostic; tested with gloo) ---------------------------------------
     def reduce_range(self, flat: torch.Tensor, start: int, end: int):
@@ -144,6 +145,8 @@ class GradExchange:
             self.reduce_range(engine.g_flat, cur, engine.total)
         self.exchange_rows_deterministic(engine.reduce_word_rows, engine.prereduce_word_rows)
         self.finish()
+        if self.scale_after_exchange != 1.0:
+            engine.g_flat.mul_(self.scale_after_exchange)
 
 
 def attach(model, optimizer=None, world_size: Optional[int] = None, group=None) -> GradExchange:
@@ -158,6 +161,9 @@ def attach(model, optimizer=None, world_size: Optional[int] = None, group=None) 
     if ex.world > 1:
         dist.broadcast(eng.p_flat, src=0, group=group)
         eng._shadow_versions = None
+        # independent dropout masks per rank (the reference's processes have independent RNG streams)
+        rank = dist.get_rank(group)
+        eng.base_seed = (eng.base_seed ^ ((rank + 1) * 0x9E3779B97F4A7C15)) & 0x7FFFFFFFFFFFFFFF
     ex.bind(eng)
     if ex.world > 1 and dev.type == "cuda":
         # leave a few SMs to NCCL: its kernels overlap the backward GEMMs, whose persistent CTAs (one per SM, static tile
@@ -166,5 +172,9 @@ def attach(model, optimizer=None, world_size: Optional[int] = None, group=None) 
         from . import ops
         ops.set_gemm_sm_limit(int(os.environ.get("CLG_DP_GEMM_SMS", "0")))
     if optimizer is not None:
-        optimizer.grad_scale = 1.0 / ex.world
+        if hasattr(optimizer, "grad_scale"):
+            optimizer.grad_scale = 1.0 / ex.world        # our AdamW: fused kernel and per-parameter path both honour it
+        else:
+            ex.scale_after_exchange = 1.0 / ex.world     # foreign optimiser: average the arena right after the exchange
+    eng.grad_scale = 1.0 / ex.world                      # clip_grad_norm_ reports / clips the AVERAGED gradient's norm
     return ex

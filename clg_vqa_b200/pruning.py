@@ -105,6 +105,14 @@ def global_magnitude_prune(model, names: Iterable[str], amount: float) -> Tuple[
     for (n, m, w, mask), new in zip(entries, new_masks):
         if mask is None:
             prune.CustomFromMask.apply(m, "weight", mask=new)
+        else:
+            # the kernel rewrote the existing `weight_mask` through its raw pointer: tell torch (version counter), so that
+            # Engine._refresh - which keys the packed mask bits and the masked bf16 shadow on (data_ptr, _version) -
+            # repacks them before the next forward
+            mask.mul_(1)
+    eng = getattr(model, "module", model).__dict__.get("_engine")
+    if eng is not None:
+        eng.invalidate_masks()
     return k, n_unpruned
 
 

@@ -78,21 +78,49 @@ def batch_for(family, B, R, ragged, seed, vocab):
                          normalize=True)
 
 
-def run_reference(ref, model, cfg, task_cfg, batch, backward=True):
+PROBE_ROW, PROBE_COL = 7, 16        # sub-sampling of the per-layer hidden-state probe
+
+
+def hidden_hooks(model, family):
+    """forward hooks that record the joint hidden state after the embeddings and after every encoder layer of the
+    UNMODIFIED reference (UC2: cat(text, regions) after each feed-forward sub-layer, encoders.py:L866-892; M3P: the
+    output of layer_norm_emb / layer_norm2[i], m3p_transformer.py:L940-948)."""
+    captured, hooks = [], []
+    if family == "uc2":
+        def cat_hook(_m, _inp, outp):
+            captured.append(torch.cat([outp[0], outp[1]], dim=1).detach().clone())
+        hooks.append(model.bert.embeddings.register_forward_hook(cat_hook))
+        for i, layer in enumerate(model.bert.encoder.layer):
+            if i % 2 == 1:
+                hooks.append(layer.register_forward_hook(cat_hook))
+    else:
+        def one_hook(_m, _inp, outp):
+            captured.append(outp.detach().clone())
+        enc = model.bert.encoder
+        hooks.append(enc.layer_norm_emb.register_forward_hook(one_hook))
+        for i in range(enc.n_layers):
+            hooks.append(enc.layer_norm2[i].register_forward_hook(one_hook))
+    return hooks, captured
+
+
+def run_reference(ref, model, cfg, task_cfg, batch, backward=True, forward_again=True):
+    """the reference's own ForwardModelsTrain (loss, score); the logits are picked up by a forward hook on the model"""
     tu = ref.task_utils
     crit = tu.LossMap["CrossEntropyLoss"]
     model.zero_grad()
-    with ref_shim.cpu_cuda_noop():
-        if backward:
-            loss, score = tu.ForwardModelsTrain(cfg, task_cfg, "cpu", "TASK15", S.batch_tuple(batch), model, crit)
-            loss.backward()
-        else:
-            with torch.no_grad():
+    got = []
+    hk = model.register_forward_hook(lambda _m, _i, outp: got.append(outp[0].detach().clone()))
+    try:
+        with ref_shim.cpu_cuda_noop():
+            if backward:
                 loss, score = tu.ForwardModelsTrain(cfg, task_cfg, "cpu", "TASK15", S.batch_tuple(batch), model, crit)
-    with torch.no_grad():
-        logits = model(batch["question"], batch["features"], batch["spatials"], "TASK15",
-                       batch["segment_ids"], batch["input_mask"], batch["image_mask"])[0]
-    return logits.detach(), float(loss), float(score)
+                loss.backward()
+            else:
+                with torch.no_grad():
+                    loss, score = tu.ForwardModelsTrain(cfg, task_cfg, "cpu", "TASK15", S.batch_tuple(batch), model, crit)
+    finally:
+        hk.remove()
+    return got[0], float(loss), float(score)
 
 
 def make_case(ref, name, spec):
@@ -128,11 +156,33 @@ def make_case(ref, name, spec):
     rows = torch.nonzero(wg.abs().sum(1) > 0).flatten()
     out["wordgrad_rows"] = rows.numpy()
     out["wordgrad_vals"] = wg[rows[:64]].numpy().copy()
-    # bf16 operand shim (fp32 accumulate) and fp64 reference: forward only
+    # bf16 operand shim (fp32 accumulate) and fp64 reference: forward only; per-layer hidden states of the shim run are
+    # sub-sampled into a probe that pins the oracle port's hidden states (the teacher-forced per-layer GPU test feeds them)
+    hooks, captured = hidden_hooks(model, family)
     with ref_shim.bf16_operand_shim():
-        lg, ls, sc = run_reference(ref, model, cfg, task_cfg, batch, backward=False)
+        lg, ls, sc = run_reference(ref, model, cfg, task_cfg, batch, backward=False, forward_again=False)
+    for h in hooks:
+        h.remove()
     out["logits_bf16shim"] = lg.numpy()
     out["loss_bf16shim"] = np.float64(ls)
+    hid = torch.stack(captured)                                    # [layers + 1, B, S, d]
+    if family == "m3p":                                            # rows past the prefix length are re-zeroed (L948)
+        n = batch["input_mask"].sum(1) + batch["image_mask"].sum(1)
+        valid = (torch.arange(hid.shape[2]).unsqueeze(0) < n.unsqueeze(1)).to(hid.dtype)
+        hid[1:] = hid[1:] * valid[None, :, :, None]
+    out["hidden_bf16shim_probe"] = hid[:, :, ::PROBE_ROW, ::PROBE_COL].contiguous().numpy()
+    # bf16 TRAINING shim: operands rounded in the forward and in the backward contractions (oracle/bf16_autograd.py)
+    with ref_shim.bf16_train_shim():
+        lgb, lsb, scb = run_reference(ref, model, cfg, task_cfg, batch, backward=True, forward_again=False)
+    assert float((lgb - lg).abs().max()) == 0.0, "train shim forward differs from the operand shim"
+    pdb = dict(model.named_parameters())
+    out["gradb_norms"] = np.array([float(pdb[n_].grad.double().norm()) if pdb[n_].grad is not None else 0.0 for n_ in names],
+                                  dtype=np.float64)
+    for k in keep:
+        if k in pdb and pdb[k].grad is not None:
+            out["gradb::" + k] = pdb[k].grad.numpy().copy()
+    out["wordgradb_vals"] = pdb[wkey].grad[rows[:64]].numpy().copy()
+    model.zero_grad()
     model.double()
     b64 = dict(batch)
     for k in ("features", "spatials", "target", "distances"):

@@ -112,3 +112,18 @@ def bf16_operand_shim():
         yield
     finally:
         F.linear, torch.matmul = lin, mm
+
+
+@contextlib.contextmanager
+def bf16_train_shim():
+    """bf16 operand rounding in the forward AND the backward contractions (oracle/bf16_autograd.py) over the
+    unmodified reference: the reference a bf16 training step's gradients are compared with."""
+    import torch
+    import torch.nn.functional as F
+    from . import bf16_autograd as ba
+    lin, mm = F.linear, torch.matmul
+    F.linear, torch.matmul = ba.linear_bf16, ba.matmul_bf16
+    try:
+        yield
+    finally:
+        F.linear, torch.matmul = lin, mm

@@ -32,11 +32,20 @@ def _r(x, mm_dtype):
     return x if mm_dtype is None else x.to(mm_dtype).to(x.dtype)
 
 
+ROUND_BWD = "bf16+bwd"      # mm_dtype value: bf16 operands in the forward AND the backward contractions
+
+
 def linear(x, w, b, mm_dtype=None):
+    if mm_dtype == ROUND_BWD:
+        from .bf16_autograd import linear_bf16
+        return linear_bf16(x, w, b)
     return F.linear(_r(x, mm_dtype), _r(w, mm_dtype), b)
 
 
 def matmul(a, b, mm_dtype=None):
+    if mm_dtype == ROUND_BWD:
+        from .bf16_autograd import matmul_bf16
+        return matmul_bf16(a, b)
     return torch.matmul(_r(a, mm_dtype), _r(b, mm_dtype))
 
 

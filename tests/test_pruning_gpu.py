@@ -57,3 +57,61 @@ def test_prune_ties_and_zero_weights():
     assert int((mask == 0).sum()) == k
     w = m.a.weight_orig.abs()
     assert float(w[mask == 0].max()) <= float(w[mask == 1].min())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_second_prune_round_reaches_the_engine(precision):
+    """IMP (train_task_prunning.py:L728-806): prune, train, prune again.  The second round rewrites the existing
+    `weight_mask` buffers in place; the engine must repack its mask bits and re-cast the masked weight shadow, i.e. the
+    next forward uses the NEW masks: gradients vanish exactly at the newly pruned positions and the logits equal those
+    of a fresh model loaded with the folded weights W_orig * M."""
+    from clg_vqa_b200 import synthetic as S, task_utils as TU
+    cfg = C.uc2_base(2, vocab_size=512)
+    task_cfg = C.gqa_task_cfg()
+    model = BertForVLTasks(cfg, task_cfg, ["TASK15"])
+    model.load_state_dict(S.synth_state_dict(model, seed=2))
+    model.set_precision(precision)
+    model.to(DEV).eval()
+    names = pruning.uc2_prunable_names(2)
+    b = S.synth_batch(4, seed=5, ragged_regions=True, vocab_size=512)
+    batch = S.batch_tuple(b)
+
+    def step():
+        model.zero_grad()
+        loss, _ = TU.ForwardModelsTrain(cfg, task_cfg, DEV, "TASK15", batch, model)
+        loss.backward()
+        with torch.no_grad():
+            return model(b["question"].to(DEV), b["features"].to(DEV), b["spatials"].to(DEV), "TASK15", b["segment_ids"].to(DEV),
+                         b["input_mask"].to(DEV), b["image_mask"].to(DEV))[0].clone()
+
+    pruning.pruning_model_uc2(model, 0.2, global_pruning=True)
+    step()
+    mods = dict(model.named_modules())
+    qmod = mods["bert.encoder.layer.0.attention_self.query"]
+    mask1 = qmod.weight_mask.clone()
+    pruning.pruning_model_uc2(model, 0.5, global_pruning=True)        # second round, in place on the existing masks
+    mask2 = qmod.weight_mask
+    newly = (mask1 == 1) & (mask2 == 0)
+    assert int(newly.sum()) > 0
+    logits = step()
+    for n in names:
+        m = mods[n]
+        assert float(m.weight_orig.grad[m.weight_mask == 0].abs().max()) == 0.0, n
+    assert float(qmod.weight_orig.grad[mask2 == 1].abs().max()) > 0.0
+    # fresh model with the folded weights (what save_sft writes): identical forward
+    folded = {}
+    for k, v in model.state_dict().items():
+        if k.endswith(".weight_mask"):
+            continue
+        if k.endswith(".weight_orig"):
+            folded[k[:-5]] = v * model.state_dict()[k[:-5] + "_mask"]
+        else:
+            folded[k] = v
+    fresh = BertForVLTasks(cfg, task_cfg, ["TASK15"])
+    fresh.load_state_dict(folded, strict=True)
+    fresh.set_precision(precision)
+    fresh.to(DEV).eval()
+    with torch.no_grad():
+        ref = fresh(b["question"].to(DEV), b["features"].to(DEV), b["spatials"].to(DEV), "TASK15", b["segment_ids"].to(DEV),
+                    b["input_mask"].to(DEV), b["image_mask"].to(DEV))[0]
+    assert torch.equal(logits, ref)
