@@ -551,7 +551,10 @@ class Engine:
         with torch.no_grad():
             self._refresh()
             training = bool(self.model.training)
-            logits = self._forward(input_txt.contiguous(), input_imgs.contiguous().float(),
+            feats = input_imgs.contiguous()
+            if not (feats.dtype == torch.bfloat16 and self.precision == "bf16"):
+                feats = feats.float()     # bf16 features are the GEMM operand as delivered: same rounding point
+            logits = self._forward(input_txt.contiguous(), feats,
                                    image_loc.contiguous().float(), task_id, token_type_ids.contiguous(),
                                    attention_mask.contiguous(), image_attention_mask.contiguous(),
                                    training, save=want_grad)
@@ -589,9 +592,13 @@ class Engine:
         feats2 = feats.view(Mr, -1)
         locs2 = locs.view(Mr, -1)
         if bf:
-            ops.cast_f32_to_bf16(feats2, ws["feat_lp"])
+            if feats2.dtype == torch.bfloat16:
+                fa = feats2                                  # delivered in the operand dtype: no cast pass, half the H2D bytes
+            else:
+                ops.cast_f32_to_bf16(feats2, ws["feat_lp"])
+                fa = ws["feat_lp"]
             ops.cast_f32_to_bf16(locs2, ws["loc_lp"])
-            fa, la = ws["feat_lp"], ws["loc_lp"]
+            la = ws["loc_lp"]
         else:
             fa, la = feats2, locs2
         nl = locs2.shape[1]
@@ -623,6 +630,7 @@ class Engine:
                 x, x_lp, kb = ws["xp"], ws["xp_lp"], ws["kbp"]
                 pack = (Mp, ws["cu"], ws["src"])
         rows = pack[0] if pack else M
+        self.last_rows = rows
         cu = pack[1] if pack else None
         nslots = len(ws["layers"])
         for l in range(Ln):

@@ -61,9 +61,13 @@ def forward(eng, ids, feats, locs, task_id, seg, tmask, imask, training, save):
     feats2 = feats.view(Mr, -1)
     locs2 = locs.view(Mr, -1)
     if bf:
-        ops.cast_f32_to_bf16(feats2, ws["feat_lp"])
+        if feats2.dtype == torch.bfloat16:
+            fa = feats2                                  # delivered in the operand dtype
+        else:
+            ops.cast_f32_to_bf16(feats2, ws["feat_lp"])
+            fa = ws["feat_lp"]
         ops.cast_f32_to_bf16(locs2, ws["loc_lp"])
-        fa, la = ws["feat_lp"], ws["loc_lp"]
+        la = ws["loc_lp"]
     else:
         fa, la = feats2, locs2
     nl = locs2.shape[1]

@@ -38,6 +38,13 @@ class GradExchange:
         self.row_vals: List[torch.Tensor] = []
         self.bucket_layers = int(os.environ.get("CLG_DP_BUCKET_LAYERS", "4"))
         self.scale_after_exchange = 1.0   # 1/world when the optimiser cannot fold the average into its gradient read
+        self.trace = None                 # list -> (name, CUDA event) marks of the exchange phases (bench.py --phases)
+
+    def _mark(self, name: str):
+        if self.trace is not None and torch.cuda.is_available():
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.trace.append((name, ev))
 
     # -- generic pieces (device-agnostic; tested with gloo) ---------------------------------------
     def reduce_range(self, flat: torch.Tensor, start: int, end: int):
@@ -69,13 +76,16 @@ class GradExchange:
             if not rows.is_contiguous():
                 rows = rows.contiguous()
             ids = prereduce(ids, rows)            # in place on rows; duplicates renamed to the padding id
+            self._mark("rows_prereduced")
         if self.world > 1:
             all_ids = torch.empty(self.world * ids.numel(), dtype=ids.dtype, device=ids.device)
             all_rows = torch.empty((self.world * rows.shape[0], rows.shape[1]), dtype=rows.dtype, device=rows.device)
             dist.all_gather_into_tensor(all_ids, ids, group=self.group)
             dist.all_gather_into_tensor(all_rows.view(-1), rows.reshape(-1), group=self.group)
             ids, rows = all_ids, all_rows
+            self._mark("rows_gathered")
         reduce_rows(ids, rows)
+        self._mark("rows_reduced")
 
     def rows_mode(self) -> bool:
         """True: the engine must not scatter its word-table gradient itself but hand the rows to add_rows()"""
@@ -131,6 +141,7 @@ class GradExchange:
         as rows; then wait (stream-wise) for all of it"""
         if not self.enabled or self.world == 1:
             return
+        self._mark("backward_done")
         from .engine import _pad
         word = engine.word_table_param()
         wslot = engine._slot_of_param[id(word)]
@@ -145,6 +156,7 @@ class GradExchange:
             self.reduce_range(engine.g_flat, cur, engine.total)
         self.exchange_rows_deterministic(engine.reduce_word_rows, engine.prereduce_word_rows)
         self.finish()
+        self._mark("allreduce_done")
         if self.scale_after_exchange != 1.0:
             engine.g_flat.mul_(self.scale_after_exchange)
 

@@ -44,3 +44,34 @@ def test_label_prior_table_rows():
         for j in (0, 1, t, A - 1, int(torch.randint(0, A, (1,), generator=g))):
             want = 0.0 if j == t else sem.get((j, t), 0.0)
             assert abs(float(rows[b, j]) - want) < 1e-7
+
+
+@pytest.mark.parametrize("family", ["uc2", "m3p"])
+def test_bf16_feature_delivery_is_bit_identical(family):
+    """region features delivered as bf16 (half the H2D bytes, no cast pass) are the GEMM operand as is - the
+    rounding point does not move, so logits, loss and every gradient are bit-identical to fp32 delivery + on-device cast."""
+    from clg_vqa_b200 import config as C, synthetic as S, task_utils as TU
+    from clg_vqa_b200.encoders import BertForVLTasks, M3PForVLTasks
+    if family == "uc2":
+        cfg = C.uc2_base(2, vocab_size=2048)
+        model = BertForVLTasks(cfg, C.gqa_task_cfg(36), ["TASK15"])
+        b = S.synth_batch(6, seed=3, ragged_regions=True, vocab_size=2048)
+    else:
+        cfg = C.m3p_base(2, n_words=2048)
+        model = M3PForVLTasks(cfg, C.gqa_task_cfg(100), ["TASK15"])
+        b = S.synth_batch(6, num_regions=100, num_locs=5, seed=3, vocab_size=2048, normalize=True)
+    tc = C.gqa_task_cfg(36 if family == "uc2" else 100)
+    model.load_state_dict(S.synth_state_dict(model, seed=4))
+    model.set_precision("bf16")
+    model.to("cuda").eval()
+    outs = []
+    for dt in (torch.float32, torch.bfloat16):
+        bb = dict(b)
+        bb["features"] = b["features"].to(dt)
+        model.zero_grad()
+        loss, _ = TU.ForwardModelsTrain(cfg, tc, "cuda", "TASK15", S.batch_tuple(bb), model)
+        loss.backward()
+        outs.append((float(loss), model.engine.g_flat.clone()))
+    assert outs[0][0] == outs[1][0]
+    d = (outs[0][1] - outs[1][1]).abs().max()
+    assert float(d) <= 1e-6 * float(outs[0][1].abs().max())        # split-K atomics order only

@@ -216,3 +216,17 @@ def test_oracle_bf16_training_gradients_match_reference(case):
             a = leaves[ck].grad.double()
             r = torch.from_numpy(g[key]).double()
             assert float((a - r).abs().max()) / max(float(r.abs().max()), 1e-3 * gscale) <= 2e-4, key
+
+
+@pytest.mark.parametrize("case", ["uc2_L2_B4", "m3p_L2_B4"])
+def test_torch_gpu_baseline_matches_oracle(case):
+    """the stock-PyTorch restatement timed by `bench.py --impl torch_gpu` (fused QKV, SDPA, F.layer_norm, F.gelu) is the
+    same function as the reference-pinned oracle (fp32, CPU, dropout off)"""
+    from oracle import torch_gpu_baseline as tb
+    g, meta = _load(case)
+    cfg, sd, b, fwd = _setup(meta)
+    with torch.no_grad():
+        fp = tb.FusedParams(sd, meta["family"], meta["layers"])
+        f = tb.uc2_forward if meta["family"] == "uc2" else tb.m3p_forward
+        lg = f(fp, cfg, *_args(b))
+    assert _rel(lg, g["logits_fp32"]) <= 1e-5
