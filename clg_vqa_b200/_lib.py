@@ -180,6 +180,8 @@ SYMBOLS = {
     "clg_embed_text_bwd": (C.c_int, [C.POINTER(EmbedTextBwdParams), c_vp]),
     "clg_gqa_prior_loss": (C.c_int, [C.POINTER(GqaLossParams), c_vp]),
     "clg_sumsq": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "clg_sumsq_sparse": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "clg_mark_rows": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "clg_adamw_step": (C.c_int, [C.POINTER(AdamWParams), c_vp]),
     "clg_cast_shadow": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "clg_cast_f32_to_bf16": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),

@@ -318,6 +318,275 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward, wide: 128 < S <= 160 (X101 features: 40 text + 100 regions; M3P)
+// The same persistent pipeline with the unit of work = (sample, head, query tile of 128 rows): K / V boxes hold up to 160
+// keys, the scores of a query row (up to 160 fp32) stay in TMEM and are walked twice (online max / sum, then the
+// normalised, rounded P), so the register file holds one 32-column chunk at a time.  In the packed layout a sample with
+// Sb <= 128 kept rows has one query tile, and the S / PV MMAs only cover the item's own key count.
+// shared memory: [3 KiB header] [nst x (Q 16 KiB | K 20 KiB | V 20 KiB)] [2 groups x P (3 x 16 KiB)]; the O staging tile
+//                aliases the group's first P block (free once the PV MMAs have completed)
+// TMEM: group g owns columns [256 g, 256 g + 256): S in [0, 160), O in [192, 256)
+// ------------------------------------------------------------------------------------------------
+static constexpr int WNP = 160;                          // key capacity
+static constexpr uint32_t WTQ = 128u * 128u;             // Q tile / one P block: 128 rows x 128 B
+static constexpr uint32_t WTK = (uint32_t)WNP * 128u;    // K / V tile
+static constexpr int WKB = 3;                            // P column blocks of 64 keys
+
+struct WideCursor {            // walks the (item, query tile) units of this CTA in issue order; every role keeps its own
+  int it, t, c;                // item index, tile index inside the item, units issued so far
+  int b, h, row0, Sb, nt;
+  int p_row0, p_end;           // row range of item it + 1, fetched while item `it` is processed (no exposed L2 round trip)
+  __device__ __forceinline__ void fetch(const AttnPipeArgs& a, int n_it, int item) {
+    if (item >= n_it) return;
+    const int bb = ((int)blockIdx.x + item * (int)gridDim.x) / a.H;
+    if (a.cu) { p_row0 = __ldg(a.cu + bb); p_end = __ldg(a.cu + bb + 1); } else { p_row0 = bb * a.S; p_end = p_row0 + a.S; }
+  }
+  __device__ __forceinline__ void adopt(const AttnPipeArgs& a, int n_it) {      // item `it` <- the prefetched range
+    if (it >= n_it) return;
+    const int w = (int)blockIdx.x + it * (int)gridDim.x;
+    b = w / a.H; h = w - b * a.H;
+    row0 = p_row0; Sb = p_end - p_row0;
+    nt = (Sb + 127) >> 7;
+    if (nt < 1) nt = 1;
+    fetch(a, n_it, it + 1);
+  }
+  __device__ __forceinline__ void init(const AttnPipeArgs& a, int n_it) { it = 0; t = 0; c = 0; p_row0 = p_end = 0; fetch(a, n_it, 0); adopt(a, n_it); }
+  __device__ __forceinline__ void next(const AttnPipeArgs& a, int n_it) {
+    ++c;
+    if (++t >= nt) { t = 0; ++it; adopt(a, n_it); }
+  }
+};
+
+enum { PB_KB = 24 };           // + stage: the producer has written the stage's key-bias row (generic stores)
+
+__global__ void __launch_bounds__(320, 1)
+attn_pipe_fwd_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const AttnPipeArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const int NST = a.nst;
+  constexpr uint32_t STAGE = WTQ + 2u * WTK;
+  const uint32_t sStage = base + 3072;
+  const uint32_t sP0 = sStage + (uint32_t)NST * STAGE;
+  auto bar = [&](int i) { return base + 8u * (uint32_t)i; };
+  volatile uint32_t* tslot = reinterpret_cast<volatile uint32_t*>(gen + 512);
+  float* kbuf = reinterpret_cast<float*>(gen + 1024);          // [nst][160] key bias x log2(e) of the stage's sample
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = a.S, H = a.H;
+  pdl_trigger();
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
+    for (int s = 0; s < 4; ++s) { mbar_init(bar(PB_FULL + s), 1); mbar_init(bar(PB_EMPTY + s), 1); mbar_init(bar(PB_KB + s), 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(bar(PB_SRDY + g), 1); mbar_init(bar(PB_PRDY + g), 4); mbar_init(bar(PB_ORDY + g), 1); mbar_init(bar(PB_TFREE + g), 4);
+      mbar_init(bar(PB_SFREE + g), 4);
+    }
+    fence_barrier_init(); fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(base + 512, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tslot;
+  pdl_wait();
+  const int n_it = ((int)blockIdx.x < a.items) ? (a.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    // ---------------- TMA producer (+ the stage's key-bias row, so that no softmax thread waits for a global load) ------
+    WideCursor u;
+    for (u.init(a, n_it); u.it < n_it; u.next(a, n_it)) {
+      const int s = u.c % NST;
+      mbar_wait(bar(PB_EMPTY + s), ((u.c / NST) & 1) ^ 1u);
+      if (elect_one()) {
+        const uint32_t st = sStage + (uint32_t)s * STAGE;
+        mbar_expect_tx(bar(PB_FULL + s), STAGE);
+        tma_load_2d(st, &tm_q, bar(PB_FULL + s), u.h * PD, u.row0 + u.t * 128);
+        tma_load_2d(st + WTQ, &tm_kv, bar(PB_FULL + s), H * PD + u.h * PD, u.row0);
+        tma_load_2d(st + WTQ + WTK, &tm_kv, bar(PB_FULL + s), 2 * H * PD + u.h * PD, u.row0);
+      }
+      float* kb = kbuf + s * WNP;
+#pragma unroll
+      for (int j = lane; j < WNP; j += 32) kb[j] = j < u.Sb ? __ldg(a.key_bias + (int64_t)u.row0 + j) * LOG2E : -INFINITY;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(PB_KB + s));       // release: orders the warp's stores (after __syncwarp) before the arrive
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    WideCursor us, up;          // next S = Q K^T to issue / next P V to issue
+    us.init(a, n_it); up.init(a, n_it);
+    while (up.it < n_it) {
+      if (up.c < us.c) {
+        const int g = up.c & 1, uu = up.c >> 1;
+        if (warp_probe(bar(PB_PRDY + g), uu & 1) && warp_probe(bar(PB_TFREE + g), (uu & 1) ^ 1u)) {
+          const int s = up.c % NST;
+          const int nk = min(WNP, (up.Sb + 15) & ~15) >> 4;       // 16-key steps that hold a key of this sample
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t sV = sStage + (uint32_t)s * STAGE + WTQ + WTK;
+            const uint32_t sP = sP0 + (uint32_t)g * WKB * WTQ;
+            constexpr uint32_t idesc = make_idesc_mn(128, PD, false, true);
+            const uint32_t tO = tmem + (uint32_t)(g * 256 + 192);
+            for (int k = 0; k < nk; ++k)
+              umma_bf16(tO, umma_desc(sP + (k >> 2) * WTQ + (k & 3) * 32, 16, 1024), umma_desc(sV + k * 2048, 8192, 1024), idesc, k > 0);
+            umma_commit(bar(PB_ORDY + g));
+            umma_commit(bar(PB_EMPTY + s));
+          }
+          __syncwarp();
+          up.next(a, n_it);
+          continue;
+        }
+      }
+      if (us.it < n_it) {
+        const int s = us.c % NST, g = us.c & 1, uu = us.c >> 1;
+        if (warp_probe(bar(PB_FULL + s), (us.c / NST) & 1) && warp_probe(bar(PB_SFREE + g), (uu & 1) ^ 1u)) {
+          const int nk = min(WNP, (us.Sb + 31) & ~31);            // score columns the softmax reads (32-column chunks)
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t st = sStage + (uint32_t)s * STAGE;
+            const uint32_t idesc = make_idesc_mn(128, nk, false, false);
+            const uint32_t tS = tmem + (uint32_t)(g * 256);
+#pragma unroll
+            for (int k = 0; k < PD / 16; ++k)
+              umma_bf16(tS, umma_desc(st + k * 32, 16, 1024), umma_desc(st + WTQ + k * 32, 16, 1024), idesc, k > 0);
+            umma_commit(bar(PB_SRDY + g));
+          }
+          __syncwarp();
+          us.next(a, n_it);
+          continue;
+        }
+      }
+    }
+  } else {
+    // ---------------- softmax groups ----------------
+    const int g = (warp - 2) >> 2;
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;                // TMEM lane == query row inside the tile
+    const int tg = (warp - 2 - 4 * g) * 32 + lane;
+    const uint32_t sP = sP0 + (uint32_t)g * WKB * WTQ;
+    uint8_t* gP = gen + (sP - base);
+    const uint32_t trow = tmem + (uint32_t)(g * 256) + ((uint32_t)(wq * 32) << 16);
+    const float scale2 = a.scale * LOG2E;
+    const bool even_rows = (S & 1) == 0;
+    WideCursor u;
+    for (u.init(a, n_it); u.it < n_it; u.next(a, n_it)) {
+      if ((u.c & 1) != g) continue;
+      const int uu = u.c >> 1;
+      const int s = u.c % NST;
+      const float* kb = kbuf + s * WNP;
+      const int Sb = u.Sb, row0 = u.row0, b = u.b, h = u.h;
+      const int q = u.t * 128 + row;                // query index inside the sample
+      const bool valid = q < Sb;
+      const bool warp_live = u.t * 128 + wq * 32 < Sb;
+      const int ncol = min(WNP, (Sb + 31) & ~31);   // == the N of this unit's S MMA
+      named_bar(1 + g, 128);                        // every thread of the group has copied the previous unit's staged tile out
+      mbar_wait(bar(PB_KB + s), (u.c / NST) & 1);   // the stage's key bias is in shared memory
+      mbar_wait(bar(PB_SRDY + g), uu & 1);
+      __syncwarp();
+      tcgen05_fence_after();
+      float m = -INFINITY, sum = 0.f;
+      if (warp_live) {
+        // pass 1: online max / sum over the row's scores (base 2); the next chunk's TMEM load is in flight while this
+        // one is reduced
+        float va[32], vb[32];
+        auto reduce_chunk = [&](float* v, int c) {
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { v[j] = fmaf(v[j], scale2, kb[c + j]); cm = fmaxf(cm, v[j]); }
+          const float mn = fmaxf(m, cm);            // finite from the first chunk on: key 0 is never masked
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s4[j & 3] += ex2f(v[j] - mn);
+          sum = fmaf(sum, ex2f(m - mn), (s4[0] + s4[1]) + (s4[2] + s4[3]));
+          m = mn;
+        };
+        tmem_ld32_nowait(trow, va);
+        for (int c = 0; c < ncol; c += 64) {
+          tmem_wait_ld_dep32(va);
+          if (c + 32 < ncol) tmem_ld32_nowait(trow + c + 32, vb);
+          reduce_chunk(va, c);
+          if (c + 32 < ncol) {
+            tmem_wait_ld_dep32(vb);
+            if (c + 64 < ncol) tmem_ld32_nowait(trow + c + 64, va);
+            reduce_chunk(vb, c + 32);
+          }
+        }
+        const float inv = valid ? 1.0f / sum : 0.f;
+        const uint64_t drow = (((uint64_t)b * H + h) * S + (valid ? q : 0)) * (uint64_t)S;
+        // pass 2: normalised probabilities, dropout, bf16 (the oracle's rounding point) -> swizzled P blocks
+        auto emit_chunk = [&](float* v, int c) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ex2f(fmaf(v[j], scale2, kb[c + j]) - m) * inv;
+#pragma unroll
+          for (int j8 = 0; j8 < 32; j8 += 8) {
+            if (a.drop.on) {
+              if (even_rows) {
+                drop8_even(a.drop, drow + c + j8, &v[j8]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[j8 + e] = drop_apply(a.drop, drow + c + j8 + e, v[j8 + e]);
+              }
+            }
+            const int col = c + j8;
+            *reinterpret_cast<uint4*>(gP + (col >> 6) * WTQ + psw_off(row, col & 63)) =
+                make_uint4(pk2(v[j8 + 0], v[j8 + 1]), pk2(v[j8 + 2], v[j8 + 3]), pk2(v[j8 + 4], v[j8 + 5]), pk2(v[j8 + 6], v[j8 + 7]));
+          }
+        };
+        tmem_ld32_nowait(trow, va);
+        for (int c = 0; c < ncol; c += 64) {
+          tmem_wait_ld_dep32(va);
+          if (c + 32 < ncol) tmem_ld32_nowait(trow + c + 32, vb);
+          emit_chunk(va, c);
+          if (c + 32 < ncol) {
+            tmem_wait_ld_dep32(vb);
+            if (c + 64 < ncol) tmem_ld32_nowait(trow + c + 64, va);
+            emit_chunk(vb, c + 32);
+          }
+        }
+      }
+      // the scores have been consumed: the S columns may be overwritten by the group's next unit
+      tcgen05_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar(PB_SFREE + g)); mbar_arrive(bar(PB_PRDY + g)); }
+      if (warp_live && valid && a.lse) a.lse[((int64_t)b * H + h) * S + q] = (m + __log2f(sum)) * LN2;
+      mbar_wait(bar(PB_ORDY + g), uu & 1);          // O in TMEM; the P blocks are free again
+      __syncwarp();
+      tcgen05_fence_after();
+      if (warp_live) {
+        float o[64];
+        tmem_ld32_nowait(trow + 192, o);
+        tmem_ld32_nowait(trow + 224, o + 32);
+        tmem_wait_ld_dep32(o);
+        tmem_wait_ld_dep32(o + 32);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(gP + psw_off(row, 8 * j)) =
+                make_uint4(pk2(o[8 * j + 0], o[8 * j + 1]), pk2(o[8 * j + 2], o[8 * j + 3]), pk2(o[8 * j + 4], o[8 * j + 5]),
+                           pk2(o[8 * j + 6], o[8 * j + 7]));
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(PB_TFREE + g));
+      // coalesced copy-out of the staged tile: 8 lanes per 128 B row
+      named_bar(1 + g, 128);
+      const int nrows = min(128, Sb - u.t * 128);
+      for (int c = tg; c < nrows * 8; c += 128) {
+        const int r = c >> 3, j = c & 7;
+        *reinterpret_cast<uint4*>(a.out + (int64_t)(row0 + u.t * 128 + r) * a.ld_out + h * PD + 8 * j) =
+            *reinterpret_cast<const uint4*>(gP + psw_off(r, 8 * j));
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward (S <= 96)
 // shared memory: [2 KiB header] [nst x (Q | K | V | dO | O)] [g=0: P (2 blocks) | dS (2 blocks)] [g=1: ...] [16 KiB slack]
 // TMEM: group g owns columns [256 g, 256 g + 256): S [0,128) | dP [128,256), then dV [0,64) | dK [64,128) | dQ [128,192)
@@ -675,8 +944,38 @@ static int launch_pipe_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const 
   return check_launch("attn_pipe_bwd_kernel");
 }
 
+static int attention_pipe_fwd_wide(const clgAttentionFwdParams& p, cudaStream_t stream) {
+  static const bool on = [] { const char* s = getenv("CLG_ATTN_WIDE"); return !(s && s[0] == '0'); }();
+  if (!on) return CLG_ERR_UNSUPPORTED;
+  if ((p.ld_ctx * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(p.ctx) & 15)) return CLG_ERR_UNSUPPORTED;
+  if (p.cu_rows && p.total_rows <= 0) return CLG_ERR_ARG;
+  const int nst = 2;
+  const int smem = 1024 + 3072 + nst * (int)(WTQ + 2 * WTK) + 2 * WKB * (int)WTQ;
+  if (smem > P_SMEM_MAX) return CLG_ERR_UNSUPPORTED;
+  const int64_t rows = p.cu_rows ? (int64_t)p.total_rows : (int64_t)p.B * p.S;   // rows beyond are zero-filled by TMA
+  CUtensorMap tq, tkv;
+  int st = make_tmap_rows(&tq, p.qkv, 3LL * p.H * PD, rows, p.ld_qkv, 128);
+  if (st != CLG_OK) return st;
+  st = make_tmap_rows(&tkv, p.qkv, 3LL * p.H * PD, rows, p.ld_qkv, WNP);
+  if (st != CLG_OK) return st;
+  AttnPipeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = p.B; a.S = p.S; a.H = p.H; a.NP = WNP; a.items = p.B * p.H; a.nst = nst;
+  a.scale = p.scale; a.key_bias = p.key_bias; a.lse = p.lse;
+  a.drop = make_drop(p.dropout);
+  a.cu = p.cu_rows; a.out = (bf16*)p.ctx; a.ld_out = p.ld_ctx;
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] { err = cudaFuncSetAttribute(attn_pipe_fwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_MAX); });
+  CLG_CUDA_OK(err, "cudaFuncSetAttribute(attn_pipe_fwd_wide)");
+  const int grid = a.items < num_sms() ? a.items : num_sms();
+  CLG_CUDA_OK(launch_pdl(attn_pipe_fwd_wide_kernel, dim3(grid), dim3(320), (size_t)smem, stream, tq, tkv, a), "launch(attn_pipe_fwd_wide)");
+  return check_launch("attn_pipe_fwd_wide_kernel");
+}
+
 // returns CLG_ERR_UNSUPPORTED when the shape is outside the pipelined kernels' range (caller falls back)
 int attention_pipe_fwd(const clgAttentionFwdParams& p, cudaStream_t stream) {
+  if (pipe_enabled() && p.dtype == CLG_BF16 && p.S > 128 && p.S <= WNP) return attention_pipe_fwd_wide(p, stream);
   if (!pipe_enabled() || p.dtype != CLG_BF16 || p.S > 128 || p.S < 1) return CLG_ERR_UNSUPPORTED;
   const int NP = (p.S + 15) / 16 * 16;
   const int ng = NP <= 96 ? 3 : 2;

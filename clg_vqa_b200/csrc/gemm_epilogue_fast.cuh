@@ -99,8 +99,9 @@ inline int classify_epilogue(const EpiArgs& e) {
     if (c_f32 && e.residual && al16(e.residual, e.ld_res, 4) && !(e.drop.on && e.drop_before_act)) return EPI_RESID;
     return EPI_GENERIC;
   }
+  // aux_out == NULL: forward-only runs (eval) do not need gelu' - the same epilogue with one output
   if (e.act == CLG_ACT_GELU_GRAD && c_bf16 && e.bias && !e.residual && !e.drop.on && !e.aux_in &&
-      e.aux_out_dtype == CLG_BF16 && al16(e.aux_out, e.ld_aux_out, 2))
+      (!e.aux_out || (e.aux_out_dtype == CLG_BF16 && al16(e.aux_out, e.ld_aux_out, 2))))
     return EPI_GELU_PAIR;
   if (e.act == CLG_ACT_MUL_AUX && c_bf16 && !e.bias && !e.residual && !e.drop.on && !e.aux_out &&
       e.aux_in_dtype == CLG_BF16 && al16(e.aux_in, e.ld_aux_in, 2))
@@ -209,16 +210,26 @@ struct FastEpi {
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) gelu_pair_fast(acc[j], acc[j], dg[j]);
-      if (lane == 0) bulk_wait_read<0>();                // previous chunk's pair of stores has read both boxes
-      __syncwarp();
-      box_store_bf16(obox(0), lane, acc);
-      box_store_bf16(obox(1), lane, dg);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(tm_c, obox(0), col, row0);
-        tma_store_2d(tm_x, obox(1), col, row0);
-        bulk_commit();
+      if (e.aux_out) {
+        if (lane == 0) bulk_wait_read<0>();              // previous chunk's pair of stores has read both boxes
+        __syncwarp();
+        box_store_bf16(obox(0), lane, acc);
+        box_store_bf16(obox(1), lane, dg);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tm_c, obox(0), col, row0);
+          tma_store_2d(tm_x, obox(1), col, row0);
+          bulk_commit();
+        }
+      } else {                                           // one output: the two boxes alternate
+        const int s = pos % 2;
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        box_store_bf16(obox(s), lane, acc);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) { tma_store_2d(tm_c, obox(s), col, row0); bulk_commit(); }
       }
     } else if (EPI == EPI_MUL_AUX) {
       float acc[32], ax[32];

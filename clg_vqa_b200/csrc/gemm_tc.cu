@@ -455,7 +455,7 @@ static int launch_tc(const clgGemmParams& p, const EpiArgs& e0, cudaStream_t str
     st = make_tmap_epi(&tc, p.C, p.c_dtype, p.N, p.M, p.ldc);
     if (st != CLG_OK) return st;
     if (EPI == EPI_RESID) st = make_tmap_epi(&tx, p.residual, CLG_F32, p.N, p.M, p.ld_res);
-    else if (EPI == EPI_GELU_PAIR) st = make_tmap_epi(&tx, p.aux_out, CLG_BF16, p.N, p.M, p.ld_aux_out);
+    else if (EPI == EPI_GELU_PAIR) { if (p.aux_out) st = make_tmap_epi(&tx, p.aux_out, CLG_BF16, p.N, p.M, p.ld_aux_out); else tx = tc; }
     else if (EPI == EPI_MUL_AUX) st = make_tmap_epi(&tx, p.aux_in, CLG_BF16, p.N, p.M, p.ld_aux_in);
     else tx = tc;
     if (st != CLG_OK) return st;

@@ -11,10 +11,24 @@ namespace clg {
 static constexpr int CHUNK = 2048;
 static constexpr int OPT_THREADS = 256;   // 8 elements per thread per chunk
 
+// one warp per 256-element block (8 consecutive floats per lane): the block's "has a non-zero gradient" bit comes for
+// free with the norm.  Blocks [sp_lo, sp_hi) (the word-embedding table: 192 M of the 281 M parameters, of which a batch
+// touches a few thousand rows) are read only where `touched` marks them (clg_mark_rows, from the token ids of the
+// backward): every other block of that range is exactly zero and contributes nothing to the norm.
+__device__ __forceinline__ float sumsq_block(const float4* g4, int64_t b, int lane, uint8_t* hot) {
+  const float4 v0 = __ldg(g4 + b * 64 + lane * 2);
+  const float4 v1 = __ldg(g4 + b * 64 + lane * 2 + 1);
+  if (hot) {
+    const bool nz = (v0.x != 0.f) | (v0.y != 0.f) | (v0.z != 0.f) | (v0.w != 0.f) | (v1.x != 0.f) | (v1.y != 0.f) |
+                    (v1.z != 0.f) | (v1.w != 0.f);
+    if (__any_sync(0xffffffffu, nz) && lane == 0) hot[b] = 1;
+  }
+  return v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w + v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
+}
+
 __global__ void __launch_bounds__(256)
-sumsq_partial_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partials, uint8_t* __restrict__ hot) {
-  // one warp per 256-element block (8 consecutive floats per lane): the block's "has a non-zero gradient" bit
-  // comes for free with the norm
+sumsq_partial_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partials, uint8_t* __restrict__ hot,
+                     int64_t sp_lo, int64_t sp_hi, const uint8_t* __restrict__ touched) {
   __shared__ float red[8];
   float acc = 0.f;
   const int lane = threadIdx.x & 31;
@@ -22,14 +36,21 @@ sumsq_partial_kernel(const float* __restrict__ g, int64_t n, float* __restrict__
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const float4* g4 = reinterpret_cast<const float4*>(g);
-  for (int64_t b = warp0; b < nblk; b += nwarps) {
-    const float4 v0 = __ldg(g4 + b * 64 + lane * 2);
-    const float4 v1 = __ldg(g4 + b * 64 + lane * 2 + 1);
-    acc += v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w + v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
-    if (hot) {
-      const bool nz = (v0.x != 0.f) | (v0.y != 0.f) | (v0.z != 0.f) | (v0.w != 0.f) | (v1.x != 0.f) | (v1.y != 0.f) |
-                      (v1.z != 0.f) | (v1.w != 0.f);
-      if (__any_sync(0xffffffffu, nz) && lane == 0) hot[b] = 1;
+  if (!touched) sp_lo = sp_hi = 0;
+  const int64_t ndense = nblk - (sp_hi - sp_lo);
+  for (int64_t i = warp0; i < ndense; i += nwarps) {
+    const int64_t b = i < sp_lo ? i : i + (sp_hi - sp_lo);
+    acc += sumsq_block(g4, b, lane, hot);
+  }
+  // sparse range: 32 blocks per warp iteration, one mark per lane
+  const int64_t ngroups = (sp_hi - sp_lo + 31) >> 5;
+  for (int64_t gi = warp0; gi < ngroups; gi += nwarps) {
+    const int64_t b = sp_lo + gi * 32 + lane;
+    unsigned live = __ballot_sync(0xffffffffu, b < sp_hi && touched[b] != 0);
+    while (live) {
+      const int l = __ffs(live) - 1;
+      live &= live - 1;
+      acc += sumsq_block(g4, sp_lo + gi * 32 + l, lane, hot);
     }
   }
   if (blockIdx.x == 0)
@@ -42,6 +63,18 @@ sumsq_partial_kernel(const float* __restrict__ g, int64_t n, float* __restrict__
     for (int w = 0; w < 8; ++w) s += red[w];
     partials[blockIdx.x] = s;
   }
+}
+
+// touched[(first_elem + id * row_elems) >> 8 ...] = 1 for every 256-element block the row of token `id` overlaps
+__global__ void __launch_bounds__(256)
+mark_rows_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t row_elems, int64_t first_elem, int64_t num_rows,
+                 int64_t skip_id, uint8_t* __restrict__ touched) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t id = ids[i];
+  if (id < 0 || id >= num_rows || id == skip_id) return;
+  const int64_t e0 = first_elem + id * row_elems, e1 = e0 + row_elems - 1;
+  for (int64_t b = e0 >> 8; b <= (e1 >> 8); ++b) touched[b] = 1;
 }
 
 __global__ void __launch_bounds__(256)
@@ -82,7 +115,10 @@ adamw_kernel(const clgAdamWParams p) {
     const int64_t rel = base - tm.start;          // element offset inside the tensor
     if (rel >= tm.numel) continue;                // tail padding of the tensor's last chunk (never written)
     const bool cold = UPDATE && p.hot && !p.hot[base >> 8];      // warp-uniform: a warp covers one 256-element block
-    if (cold && !(tm.wd > 0.f)) continue;                         // g = m = v = 0 and no decay: nothing changes
+    // g = m = v = 0: the update reduces to the decoupled decay p <- fma(-lr*wd, p, p).  Below 2^-25 the product is under
+    // half an ulp of p, so the rounded result IS p (bit-identical to the dense update): with the reference's settings
+    // (lr <= 1e-4, weight decay 1e-4, train_task.py:L249-267) the untouched word-embedding rows cost no traffic at all
+    if (cold && !(tm.lr * tm.wd >= 2.98023224e-8f)) continue;
     float pv[8];
     {
       const float4 a = *reinterpret_cast<const float4*>(p.p + base);
@@ -151,20 +187,38 @@ adamw_kernel(const clgAdamWParams p) {
 
 }  // namespace clg
 
-extern "C" int clg_sumsq(const float* g, int64_t n, float* partials, int32_t num_partials, float* out, uint8_t* hot,
-                         clgStream_t stream) {
+extern "C" int clg_sumsq_sparse(const float* g, int64_t n, float* partials, int32_t num_partials, float* out, uint8_t* hot,
+                                int64_t sparse_lo, int64_t sparse_hi, const uint8_t* touched, clgStream_t stream) {
   using namespace clg;
   if (!g || !partials || !out || n < 0 || num_partials <= 0) return CLG_ERR_ARG;
+  if (touched && (sparse_lo < 0 || sparse_hi < sparse_lo || sparse_hi > (n >> 8))) return CLG_ERR_ARG;
   int st = require_sm100();
   if (st != CLG_OK) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int grid = num_sms() * 4;
   if (grid > num_partials) grid = num_partials;
-  sumsq_partial_kernel<<<grid, 256, 0, s>>>(g, n, partials, hot);
+  sumsq_partial_kernel<<<grid, 256, 0, s>>>(g, n, partials, hot, sparse_lo, sparse_hi, touched);
   st = check_launch("sumsq_partial_kernel");
   if (st != CLG_OK) return st;
   sumsq_final_kernel<<<1, 256, 0, s>>>(partials, grid, out);
   return check_launch("sumsq_final_kernel");
+}
+
+extern "C" int clg_sumsq(const float* g, int64_t n, float* partials, int32_t num_partials, float* out, uint8_t* hot,
+                         clgStream_t stream) {
+  return clg_sumsq_sparse(g, n, partials, num_partials, out, hot, 0, 0, nullptr, stream);
+}
+
+extern "C" int clg_mark_rows(const int64_t* ids, int64_t n, int64_t row_elems, int64_t first_elem, int64_t num_rows,
+                             int64_t skip_id, uint8_t* touched, clgStream_t stream) {
+  using namespace clg;
+  if (!ids || !touched || n < 0 || row_elems <= 0 || first_elem < 0 || num_rows < 0) return CLG_ERR_ARG;
+  int st = require_sm100();
+  if (st != CLG_OK) return st;
+  if (n == 0) return CLG_OK;
+  mark_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ids, n, row_elems, first_elem,
+                                                                                                 num_rows, skip_id, touched);
+  return check_launch("mark_rows_kernel");
 }
 
 extern "C" int clg_adamw_step(const clgAdamWParams* p, clgStream_t stream) {

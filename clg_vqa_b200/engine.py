@@ -248,8 +248,14 @@ class Engine:
         _optim.register_engine(self)
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=device)
         # one byte per 256 arena elements: 1 = the block has received a non-zero gradient at some point (optim.py)
-        self._hot = torch.ones(self.p_flat.numel() // 256, dtype=torch.uint8, device=device)
+        self._hot = torch.zeros(self.p_flat.numel() // 256, dtype=torch.uint8, device=device)
         self._hot_valid = False
+        # per-backward marks of the word-table blocks that received gradient rows (ops.mark_rows): the norm pass reads only
+        # those blocks of the 768 MB table gradient (optim.clip_grad_norm_); cleared whenever the arena is cleared
+        wslot = self._slot_of_param[id(self.word_table_param())]
+        self._table_blocks = (wslot.start // 256, (wslot.start + wslot.numel + 255) // 256)
+        self._touched = torch.zeros(self.p_flat.numel() // 256, dtype=torch.uint8, device=device)
+        self._touch_valid = False
 
     def _build_tables(self, lr_wd=None):
         """chunk -> tensor table and the clgTensorMeta array (lr / wd filled by the optimiser)."""
@@ -620,7 +626,7 @@ class Engine:
         # pooler takes token 0, which is always kept) and hence their gradients vanish identically.  The layers then run
         # on Mp = sum(kept) rows instead of B*S; the pipelined attention kernels read the per-sample row ranges.
         pack = None
-        if bf and self.pack_enabled and Ln > 0 and S <= (96 if save else 128):
+        if bf and self.pack_enabled and Ln > 0 and S <= (96 if save else 160):   # pipelined attention: bwd S <= 96, fwd S <= 160
             ops.pack_index(tmask, imask, ws["cu"], ws["src"])
             Mp = int(ws["cu"][B])                     # the one host read of the step (launch shapes depend on it)
             if Mp < M:
@@ -640,7 +646,7 @@ class Engine:
             x, x_lp = self._layer_fwd(lw, x, x_lp, kb, B, S, sa.query, so.dense, so.LayerNorm, fi.dense, fo.dense,
                                       fo.LayerNorm, eps, 0.125, self._site(2 + 4 * l, p_a, training),
                                       self._site(3 + 4 * l, p_h, training), self._site(4 + 4 * l, p_h, training), bf,
-                                      rows=rows, cu=cu)
+                                      rows=rows, cu=cu, save=save)
             self._probe_capture(l, x, B, S, pack)
         self._probe_inject(Ln, x, x_lp, B, S, pack)
         logits = self._head_fwd(ws, x_lp, B, S, task_id, self.pooler.dense, self.pool_act,
@@ -651,7 +657,7 @@ class Engine:
         return logits
 
     def _layer_fwd(self, lw, x, x_lp, kb, B, S, qmod, omod, ln1, f1mod, f2mod, ln2, eps, scale, site_p, site_o, site_f, bf,
-                   row_valid=None, rows=None, cu=None):
+                   row_valid=None, rows=None, cu=None, save=True):
         """rows: token rows actually present (B*S, or the packed count with cu = per-sample row ranges)"""
         d, F, H = self.d, self.F, self.H
         M = B * S if rows is None else rows
@@ -662,8 +668,9 @@ class Engine:
                           mean=lw["m1"], rstd=lw["r1"], rows=M)
         # bf16 mode saves gelu'(u) (one shared exponential in the epilogue) so the backward epilogue is a multiply;
         # the fp32 correctness mode saves u and evaluates the exact erf / exp derivative in the backward
+        # (forward-only runs do not store gelu': same epilogue, one output)
         ops.gemm(lw["x1_lp"], self._w(f1mod, F, d), lw["h"], bias=self._bias(f1mod, F),
-                 act=ops.ACT_GELU_GRAD if bf else ops.ACT_GELU, aux_out=lw["u"], M=M)
+                 act=ops.ACT_GELU_GRAD if bf else ops.ACT_GELU, aux_out=lw["u"] if (save or not bf) else None, M=M)
         ops.gemm(lw["h"], self._w(f2mod, d, F), lw["y2"], bias=self._bias(f2mod, d), residual=lw["x1"], dropout=site_f, M=M)
         ops.layernorm_fwd(lw["y2"], ln2.weight.data, ln2.bias.data, eps, y=lw["x2"], y_lowp=lw["x2_lp"] if bf else None,
                           mean=lw["m2"], rstd=lw["r2"], row_valid=row_valid, valid_post=row_valid is not None, rows=M)
@@ -707,6 +714,9 @@ class Engine:
         if dropped or self.grads_consumed:
             if not self.grads_zeroed:
                 self.g_flat.zero_()
+            lo, hi = self._table_blocks
+            self._touched[lo:hi].zero_()
+            self._touch_valid = True        # from here on every write into the table gradient is marked (mark_word_rows)
             for s in self.slots:
                 o = s.start
                 for p in s.params:
@@ -876,6 +886,8 @@ class Engine:
                            type_row0_has_total=True)
         if rows_mode:
             self.dp.add_rows(sv["ids"], ws["de_txt"])
+        else:
+            self.mark_word_rows(sv["ids"])
         # ---- region embeddings
         ops.layernorm_bwd(dx, ws["t2"], E.v_LayerNorm.weight.data, ws["m_v"], ws["r_v"], dx=ws["ds"],
                           dgamma=self.grad_view(E.v_LayerNorm.weight), dbeta=self.grad_view(E.v_LayerNorm.bias),
@@ -898,6 +910,13 @@ class Engine:
             return self.model.bert.embeddings.word_embeddings.weight
         return self.model.bert.encoder.embeddings.weight
 
+    def mark_word_rows(self, ids: torch.Tensor):
+        """record which blocks of the word-table gradient the rows of `ids` touch (see adopt / optim.clip_grad_norm_)"""
+        word = self.word_table_param()
+        wslot = self._slot_of_param[id(word)]
+        pad = int(self.cfg.pad_token_id) if self.family == "uc2" else int(getattr(self.cfg, "pad_index", 1))
+        ops.mark_rows(ids, word.shape[1], wslot.start, word.shape[0], pad, self._touched)
+
     def reduce_word_rows(self, ids: torch.Tensor, rows: torch.Tensor):
         """word-table gradient += the (token id, gradient row) list, reduced deterministically: sorted by id (stable), one
         warp per distinct id summing its rows in list order.  Called by parallel.GradExchange with the all-gathered list."""
@@ -905,6 +924,7 @@ class Engine:
         pad = int(self.cfg.pad_token_id) if self.family == "uc2" else int(getattr(self.cfg, "pad_index", 1))
         sorted_ids, order = torch.sort(ids, stable=True)           # index bookkeeping only; no host sync
         ops.segment_sum_rows(rows, order, sorted_ids, gword, pad)
+        self.mark_word_rows(ids)
 
     def prereduce_word_rows(self, ids: torch.Tensor, rows: torch.Tensor):
         """local step before the all-gather: duplicate token ids of this rank are summed into one row (in place) and the

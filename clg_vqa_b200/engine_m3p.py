@@ -85,22 +85,43 @@ def forward(eng, ids, feats, locs, task_id, seg, tmask, imask, training, save):
     ops.layernorm_fwd(ws["e_joint"], ln.weight.data, ln.bias.data, eps, y=ws["x0"], y_lowp=ws["x0_lp"] if bf else None,
                       mean=ws["m_e"], rstd=ws["r_e"], row_valid=ws["row_valid"], valid_pre=True,
                       dropout=eng._site(0, p_h, training))
-    x, x_lp = ws["x0"], ws["x0_lp"]
+    x, x_lp, kb = ws["x0"], ws["x0_lp"], ws["kb"]
     eng._probe_capture("emb", x, B, S, None)
+    # Packing (forward-only runs: the S <= 160 pipelined attention forward reads the packed layout, the wide backward does
+    # not yet): the prefix mask keeps the first n = n_img + n_txt rows of [regions ; text] (get_masks, m3p_transformer.py
+    # L59-78); rows past it are masked keys whose hidden state is re-zeroed after every layer - never observable, since
+    # the pooler reads row 0.  Dropping them is exact, as for UC2 (engine._forward).
+    pack = None
+    row_valid = ws["row_valid"]
+    if bf and eng.pack_enabled and not save and Ln > 0 and S <= 160:
+        n_valid = tmask.sum(1) + imask.sum(1)
+        prefix = (torch.arange(S, device=eng.device).unsqueeze(0) < n_valid.unsqueeze(1)).to(torch.int64)
+        ops.pack_index(prefix[:, :R].contiguous(), prefix[:, R:].contiguous(), ws["cu"], ws["src"])
+        Mp = int(ws["cu"][B])
+        if Mp < M:
+            ops.rows_gather(x, ws["src"], ws["xp"], n=Mp)
+            ops.rows_gather(x_lp, ws["src"], ws["xp_lp"], n=Mp)
+            ops.rows_gather(kb.view(M, 1), ws["src"], ws["kbp"], n=Mp)
+            x, x_lp, kb = ws["xp"], ws["xp_lp"], ws["kbp"]
+            pack = (Mp, ws["cu"], ws["src"])
+            row_valid = None                      # every kept row is inside the prefix
+    rows = pack[0] if pack else None
+    eng.last_rows = rows if pack else M
+    cu = pack[1] if pack else None
     nslots = len(ws["layers"])
     for l in range(Ln):
         a = enc.attentions[l]
         lw = ws["layers"][l % nslots]
-        eng._probe_inject(l, x, x_lp, B, S, None)
-        x, x_lp = eng._layer_fwd(lw, x, x_lp, ws["kb"], B, S, a.q_lin, a.out_lin, enc.layer_norm1[l], enc.ffns[l].lin1,
+        eng._probe_inject(l, x, x_lp, B, S, pack)
+        x, x_lp = eng._layer_fwd(lw, x, x_lp, kb, B, S, a.q_lin, a.out_lin, enc.layer_norm1[l], enc.ffns[l].lin1,
                                  enc.ffns[l].lin2, enc.layer_norm2[l], eps, 0.125, eng._site(2 + 4 * l, p_a, training),
                                  eng._site(3 + 4 * l, p_h, training), eng._site(4 + 4 * l, p_h, training), bf,
-                                 row_valid=ws["row_valid"])
-        eng._probe_capture(l, x, B, S, None)
-    eng._probe_inject(Ln, x, x_lp, B, S, None)
+                                 row_valid=row_valid, rows=rows, cu=cu, save=save)
+        eng._probe_capture(l, x, B, S, pack)
+    eng._probe_inject(Ln, x, x_lp, B, S, pack)
     logits = eng._head_fwd(ws, x_lp, B, S, task_id, eng.pooler.dense, eng.pool_act,
                            eng._site(2 + 4 * Ln, float(eng.model.dropout.p), training),
-                           float(getattr(cfg, "layer_norm_eps", 1e-12)), bf)
+                           float(getattr(cfg, "layer_norm_eps", 1e-12)), bf, pack=pack)
     if save:
         eng._saved = dict(ws=ws, ids=ids, seg=seg, fa=fa, la=la, task=task_id, training=training, ticket=eng._ticket,
                           B=B, T=T, R=R, feats=feats, locs=locs)
@@ -148,6 +169,8 @@ def backward(eng, dl, sv):
                        pad_id=int(getattr(cfg, "pad_index", 1)), dout_map=rowmap(T, R, S), pos_mode=1, pos_base=R)
     if rows_mode:
         eng.dp.add_rows(sv["ids"], de.view(B, S, d)[:, R:, :].reshape(B * T, d))
+    else:
+        eng.mark_word_rows(sv["ids"])
     # region rows: positions 0..R-1
     ops.embed_text_bwd(ws["arange_r"], None, de, None, gpos, None, pad_id=-1, dout_map=rowmap(R, 0, S), pos_mode=1,
                        pos_base=0)

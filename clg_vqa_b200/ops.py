@@ -293,11 +293,29 @@ def gqa_prior_loss(logits, target, dist, *, dlogits=None, row_buf, out, pred=Non
     _count(2)
 
 
-def sumsq(g_flat, partials, out, hot=None):
+def sumsq(g_flat, partials, out, hot=None, sparse=None):
+    """sparse = (first block, end block, touched map): blocks of that range are read only where marked (clg_sumsq_sparse)"""
     _need_cuda(g_flat, partials, out)
-    L.check(L.load().clg_sumsq(g_flat.data_ptr(), g_flat.numel(), partials.data_ptr(), partials.numel(),
-                               out.data_ptr(), _ptr(hot), _stream()), "clg_sumsq")
+    if sparse is None:
+        L.check(L.load().clg_sumsq(g_flat.data_ptr(), g_flat.numel(), partials.data_ptr(), partials.numel(),
+                                   out.data_ptr(), _ptr(hot), _stream()), "clg_sumsq")
+    else:
+        lo, hi, touched = sparse
+        L.check(L.load().clg_sumsq_sparse(g_flat.data_ptr(), g_flat.numel(), partials.data_ptr(), partials.numel(),
+                                          out.data_ptr(), _ptr(hot), int(lo), int(hi), touched.data_ptr(), _stream()),
+                "clg_sumsq_sparse")
     _count(2)
+
+
+def mark_rows(ids, row_elems, first_elem, num_rows, skip_id, touched):
+    """touched[block] = 1 for the 256-element arena blocks under the gradient rows of `ids` (int64)"""
+    _need_cuda(ids, touched)
+    ids = ids.reshape(-1)
+    if ids.dtype != torch.int64 or not ids.is_contiguous():
+        ids = ids.to(torch.int64).contiguous()
+    L.check(L.load().clg_mark_rows(ids.data_ptr(), ids.numel(), int(row_elems), int(first_elem), int(num_rows), int(skip_id),
+                                   touched.data_ptr(), _stream()), "clg_mark_rows")
+    _count(1)
 
 
 def adamw_step(p_flat, g_flat, m_flat, v_flat, chunk_tensor, tensors_dev, *, sumsq=None, max_norm=1.0, gscale=1.0,

@@ -68,7 +68,8 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0):
     eng._sumsq.zero_()
     # the norm pass also marks which 256-element blocks of the gradient arena hold a non-zero (eng._hot); the fused
     # AdamW of THIS gradient then skips the m / v traffic of blocks that have never received one
-    ops.sumsq(eng.g_flat, eng._partials, eng._sumsq, hot=eng._hot)
+    sparse = (eng._table_blocks[0], eng._table_blocks[1], eng._touched) if eng._touch_valid else None
+    ops.sumsq(eng.g_flat, eng._partials, eng._sumsq, hot=eng._hot, sparse=sparse)
     eng._hot_valid = True
     _PENDING_CLIP[id(eng)] = float(max_norm)
     # the norm of the AVERAGED gradient (what the reference logs and clips after apex's 1/world)
@@ -108,8 +109,10 @@ class AdamW(Optimizer):
             m = torch.zeros_like(eng.p_flat)
             v = torch.zeros_like(eng.p_flat)
             fs = dict(engine=eng, p_flat_ptr=eng.p_flat.data_ptr(), m=m, v=v, step=0)
-            eng._hot.zero_()          # fresh moments: every block is cold until it sees a gradient
-            eng._hot_valid = False
+            # fresh moments (m = v = 0): a block may take the cold shortcut iff it has not held a non-zero gradient since.
+            # eng._hot (zeroed when the arenas were built, only ever set by the norm pass) is a superset of those blocks -
+            # it already holds the marks of the gradient this very step consumes (clip_grad_norm_ ran before us) - so it is
+            # kept as it is; marks left by an earlier optimiser only make some blocks take the dense (always correct) path
             # carry over per-parameter state created by an earlier load_state_dict
             for g in self.param_groups:
                 for p in g["params"]:

@@ -341,13 +341,23 @@ typedef struct {
   const uint8_t* hot;                /* optional [n/256]: 0 = the block's g, m, v are all zero (marked by clg_sumsq on THIS
                                         gradient): only the decoupled decay p -= lr*wd*p is applied - bit-identical to the
                                         dense update, 8 instead of 28 bytes of HBM traffic per parameter (the word-embedding
-                                        rows a batch never touches) */
+                                        rows a batch never touches); when lr*wd < 2^-25 that decay rounds to p itself and
+                                        the block is not touched at all */
 } clgAdamWParams;
 
 /* out[0] += sum g^2 (two deterministic passes).  hot (optional, [n/256] bytes): hot[b] = 1 for every 256-element block
  * of g that holds a non-zero (never cleared here): blocks that have never seen a gradient have m = v = 0 and are
  * updated by the shortcut below. */
 int clg_sumsq(const float* g, int64_t n, float* partials, int32_t num_partials, float* out, uint8_t* hot, clgStream_t stream);
+/* as clg_sumsq, but the 256-element blocks [sparse_lo, sparse_hi) of the arena (the word-embedding table's gradient) are
+ * read only where touched[b] != 0: every other block of that range must be exactly zero (its rows were not in the batch).
+ * clg_mark_rows sets the marks from the token ids of a backward: the blocks overlapped by the gradient row of every id
+ * (row `id` starts at element first_elem + id * row_elems; ids outside [0, num_rows) and id == skip_id - the padding
+ * row, which receives no gradient - are ignored).  The caller clears `touched` when it clears the gradient. */
+int clg_sumsq_sparse(const float* g, int64_t n, float* partials, int32_t num_partials, float* out, uint8_t* hot,
+                     int64_t sparse_lo, int64_t sparse_hi, const uint8_t* touched, clgStream_t stream);
+int clg_mark_rows(const int64_t* ids, int64_t n, int64_t row_elems, int64_t first_elem, int64_t num_rows, int64_t skip_id,
+                  uint8_t* touched, clgStream_t stream);
 int clg_adamw_step(const clgAdamWParams* p, clgStream_t stream);
 size_t clg_sizeof_adamw_params(void);
 size_t clg_sizeof_tensor_meta(void);

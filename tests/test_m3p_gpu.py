@@ -111,3 +111,36 @@ def test_m3p_bf16_training_step_runs():
     assert torch.isfinite(loss)
     assert torch.equal(dead, model.bert.encoder.encoder_attn[0].q_lin.weight.detach())          # never moves (no gradient)
     assert not torch.equal(livew, model.bert.encoder.attentions[0].q_lin.weight.detach())
+
+
+@pytest.mark.parametrize("family", ["m3p", "uc2"])
+def test_eval_packed_rows_equal_padded_rows_s140(family):
+    """xGQA eval shape (40 text + 100 regions, S = 140): forward-only runs drop the masked positions (M3P: everything past the
+    prefix length) and use the S <= 160 pipelined attention on the packed layout; logits must equal the padded run up to
+    the accumulation-order noise of the bf16 pipeline, argmax identical on safe margins."""
+    from clg_vqa_b200.encoders import BertForVLTasks
+    B, R = 24, 100
+    if family == "m3p":
+        cfg = C.m3p_base(2, n_words=4096)
+        model = M3PForVLTasks(cfg, C.gqa_task_cfg(R), ["TASK15"])
+        b = S.synth_batch(B, num_regions=R, num_locs=5, seed=21, vocab_size=4096, normalize=True)
+    else:
+        cfg = C.uc2_base(2, vocab_size=4096)
+        model = BertForVLTasks(cfg, C.gqa_task_cfg(R), ["TASK15"])
+        b = S.synth_batch(B, num_regions=R, num_locs=7, seed=21, vocab_size=4096, ragged_regions=True)
+    model.load_state_dict(S.synth_state_dict(model, seed=6))
+    model.set_precision("bf16")
+    model.to(DEV).eval()
+    outs = {}
+    for pack in (True, False):
+        model.engine.pack_enabled = pack
+        with torch.no_grad():
+            outs[pack] = model(b["question"].to(DEV), b["features"].to(DEV), b["spatials"].to(DEV), "TASK15",
+                               b["segment_ids"].to(DEV), b["input_mask"].to(DEV), b["image_mask"].to(DEV))[0].float().clone()
+        if pack:
+            assert model.engine.last_rows < B * 140          # the packed path really ran
+    assert _rel(outs[True], outs[False]) <= 5e-3
+    ref = outs[False].cpu()
+    top2 = torch.topk(ref, 2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 5e-3 * ref.abs().max()
+    assert torch.equal(outs[True].argmax(1).cpu()[safe], ref.argmax(1)[safe])

@@ -86,7 +86,8 @@ def test_layernorm_generic_width(N):
     assert _rel(dx, xr.grad) < 1e-5 and _rel(dg, gr.grad) < 1e-5 and _rel(db, br.grad) < 1e-5
 
 
-def test_adamw_cold_blocks_bit_identical_to_dense():
+@pytest.mark.parametrize("wd", [1e-4, 5e-2])
+def test_adamw_cold_blocks_bit_identical_to_dense(wd):
     """Blocks of 256 elements that have never received a gradient (word-embedding rows no batch has touched) take the
     shortcut p -= lr*wd*p; the result must be bit-identical to the dense update, and the norm pass must mark exactly
     the blocks with non-zero gradients."""
@@ -103,7 +104,9 @@ def test_adamw_cold_blocks_bit_identical_to_dense():
     chunk_tensor[:(k + L.CHUNK - 1) // L.CHUNK] = 0
     chunk_tensor[start2 // L.CHUNK] = 1
     metas = (L.TensorMeta * 2)()
-    metas[0] = L.TensorMeta(4e-5, 1e-4, 0, -1, 0, k)
+    # wd = 1e-4: lr*wd = 4e-9 < 2^-25, the decay of a cold block rounds to the identity and the block is skipped entirely;
+    # wd = 5e-2: lr*wd = 2e-6, cold blocks take the read-decay-write shortcut.  Both must equal the dense update bit for bit.
+    metas[0] = L.TensorMeta(4e-5, wd, 0, -1, 0, k)
     metas[1] = L.TensorMeta(4e-5, 0.0, -1, -1, start2, k2)
     chunk_tensor = chunk_tensor.to(DEV)
     tens = torch.frombuffer(bytearray(bytes(metas)), dtype=torch.uint8).to(DEV)
@@ -168,3 +171,41 @@ def test_segment_sum_rows_deterministic_reduction():
     s_ids, order = torch.sort(ids.to(DEV), stable=True)
     ops.segment_sum_rows(rows.to(DEV), order, s_ids, table2, pad)
     assert float((table2.double().cpu() - ref).abs().max()) < 1e-3
+
+
+def test_sumsq_sparse_reads_only_marked_blocks():
+    """clg_sumsq_sparse + clg_mark_rows: the norm of an arena whose word-table range is zero except for the rows of the
+    batch's token ids equals the dense norm; unmarked blocks are really skipped (a poisoned unmarked block is not seen)."""
+    rows, dim = 5000, 768
+    first = 4096                                      # table starts at element 4096 (block 16)
+    n = first + rows * dim + 4096
+    n = n // 256 * 256
+    torch.manual_seed(5)
+    g = torch.zeros(n, device=DEV)
+    g[:first] = torch.randn(first, device=DEV)
+    g[first + rows * dim:] = torch.randn(n - first - rows * dim, device=DEV)
+    ids = torch.randint(0, rows, (64, 40), device=DEV)
+    ids[:, 30:] = 1                                   # padding id: never receives a gradient
+    tab = g[first:first + rows * dim].view(rows, dim)
+    uniq = torch.unique(ids[ids != 1])
+    tab[uniq] = torch.randn(uniq.numel(), dim, device=DEV)
+    touched = torch.zeros(n // 256, dtype=torch.uint8, device=DEV)
+    ops.mark_rows(ids, dim, first, rows, 1, touched)
+    lo, hi = first // 256, (first + rows * dim) // 256
+    want = torch.zeros(rows, dtype=torch.bool, device=DEV); want[uniq] = True
+    assert torch.equal(touched[lo:hi].view(rows, 3).bool(), want[:, None].expand(rows, 3))
+    assert int(touched[:lo].sum()) == 0 and int(touched[hi:].sum()) == 0
+    partials = torch.zeros(1024, device=DEV)
+    dense = torch.zeros(1, device=DEV); sparse = torch.zeros(1, device=DEV)
+    hot_d = torch.zeros(n // 256, dtype=torch.uint8, device=DEV); hot_s = torch.zeros_like(hot_d)
+    ops.sumsq(g, partials, dense, hot=hot_d)
+    ops.sumsq(g, partials, sparse, hot=hot_s, sparse=(lo, hi, touched))
+    ref = float(g.double().pow(2).sum())
+    assert abs(float(dense) - ref) <= 1e-5 * ref and abs(float(sparse) - ref) <= 1e-5 * ref
+    assert torch.equal(hot_d, hot_s)
+    # an unmarked block is not read at all
+    free = int(torch.nonzero(~want)[0])
+    tab[free] = float("nan")
+    sparse.zero_()
+    ops.sumsq(g, partials, sparse, sparse=(lo, hi, touched))
+    assert abs(float(sparse) - ref) <= 1e-5 * ref

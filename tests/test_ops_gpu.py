@@ -462,7 +462,7 @@ def test_utilities():
     assert torch.equal(w2, w * mask)
 
 
-@pytest.mark.parametrize("S,B", [(76, 5), (140, 5), (128, 5), (33, 5), (76, 67), (96, 40), (16, 30)])
+@pytest.mark.parametrize("S,B", [(76, 5), (140, 5), (128, 5), (33, 5), (76, 67), (96, 40), (16, 30), (140, 67), (129, 9)])
 def test_attention_tc_matches_ffma(S, B):
     """tcgen05 attention (bf16; backend 0 = persistent pipelined kernels where the shape allows, 2 = one CTA per head)
     against the FFMA kernel on the same inputs, incl. identical dropout masks.  B = 67 / 40 / 30 give the persistent
@@ -556,3 +556,47 @@ def test_attention_packed_rows_match_padded(S, B):
     back = torch.zeros_like(qkv)
     ops.rows_scatter(qp, src, back, n=Mp)
     assert torch.equal(back[sel], qkv[sel]) and float(back[~keep.view(-1)].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("S,B,T", [(140, 37, 40), (160, 13, 40), (133, 50, 33)])
+def test_attention_wide_packed_forward_matches_padded(S, B, T):
+    """S in (128, 160] (X101 features / M3P): the pipelined forward reads the packed layout - samples with <= 128 kept rows
+    have one query tile, longer ones two; context rows and log-sum-exp equal the padded computation row for row."""
+    H = 12
+    R = S - T
+    D = H * 64
+    g = torch.Generator(device="cpu").manual_seed(17)
+    tlen = torch.randint(3, T + 1, (B,), generator=g)
+    rlen = torch.randint(R - 30, R + 1, (B,), generator=g)
+    tlen[0], rlen[0] = T, R                                  # a full-length sample (two query tiles)
+    tlen[1], rlen[1] = 3, R - 30                             # a short one (one tile)
+    tm = (torch.arange(T)[None] < tlen[:, None]).long().to(DEV)
+    im = (torch.arange(R)[None] < rlen[:, None]).long().to(DEV)
+    kb = torch.empty(B, S, device=DEV)
+    ops.build_key_bias(tm, im, kb)
+    qkv = _rand(B * S, 3 * D, dtype=torch.bfloat16, seed=195)
+    ctx0 = torch.zeros(B * S, D, device=DEV, dtype=torch.bfloat16); lse0 = torch.zeros(B, H, S, device=DEV)
+    ops.attention_fwd(qkv, kb, ctx0, lse0, B, S, H, 0.125)
+    cu = torch.zeros(B + 1, device=DEV, dtype=torch.int32); src = torch.zeros(B * S, device=DEV, dtype=torch.int32)
+    ops.pack_index(tm, im, cu, src)
+    Mp = int(cu[-1])
+    lens = (cu[1:] - cu[:-1]).cpu()
+    assert int(lens.max()) > 128 and int(lens.min()) <= 128
+    qp = torch.full_like(qkv, float("nan")); kbp = torch.full((B * S, 1), float("nan"), device=DEV)
+    ops.rows_gather(qkv, src, qp, n=Mp); ops.rows_gather(kb.view(-1, 1), src, kbp, n=Mp)
+    qp[Mp:] = 0                                              # rows past the packed end are read by the last K / V boxes
+    ctxp = torch.full((B * S, D), float("nan"), device=DEV, dtype=torch.bfloat16); lsep = torch.zeros(B, H, S, device=DEV)
+    ops.attention_fwd(qp, kbp, ctxp, lsep, B, S, H, 0.125, cu_rows=cu, total_rows=Mp)
+    sel = src[:Mp].long()
+    assert bool(torch.isfinite(ctxp[:Mp].float()).all())
+    assert bool(torch.isnan(ctxp[Mp:].float()).all())        # nothing is written past the packed rows
+    assert _rel(ctxp[:Mp], ctx0[sel]) < 1e-2
+    # log-sum-exp of the kept query rows ([B, H, S] indexed by the position inside the packed sample)
+    keep = torch.cat([tm, im], 1).bool(); keep[:, 0] = True
+    for b in (0, 1, B - 1):
+        pos = torch.nonzero(keep[b]).flatten()
+        assert _rel(lsep[b, :, :pos.numel()], lse0[b][:, pos]) < 1e-5
+    # with dropout: finite, and a different mask than without
+    ctxd = torch.zeros_like(ctxp)
+    ops.attention_fwd(qp, kbp, ctxd, lsep, B, S, H, 0.125, DropSite(0.1, 5, 1 << 41), cu_rows=cu, total_rows=Mp)
+    assert bool(torch.isfinite(ctxd[:Mp].float()).all()) and float((ctxd[:Mp].float() - ctxp[:Mp].float()).abs().max()) > 0
