@@ -588,6 +588,8 @@ class Engine:
         p_a = float(cfg.attention_probs_dropout_prob)
 
         ops.build_key_bias(tmask, imask, ws["kb"])
+        if save and self.dp is not None and self.dp.rows_mode():
+            self.dp.plan_rows(ids, int(cfg.pad_token_id))       # id-only half of the word-row exchange, off the backward's tail
         # ---- text embeddings (embeddings.py:L640-654)
         ops.embed_text_fwd(ids, seg, E.word_embeddings.weight.data, E.position_embeddings.weight.data,
                            E.new_token_type_embeddings.weight.data, ws["e_txt"], pad_id=cfg.pad_token_id)
@@ -886,6 +888,7 @@ class Engine:
                            type_row0_has_total=True)
         if rows_mode:
             self.dp.add_rows(sv["ids"], ws["de_txt"])
+            self.dp.rows_ready(self)                # pre-reduction + all-gather start here, under the region half below
         else:
             self.mark_word_rows(sv["ids"])
         # ---- region embeddings

@@ -58,6 +58,8 @@ def forward(eng, ids, feats, locs, task_id, seg, tmask, imask, training, save):
         ws["r_e"] = torch.empty(M, dtype=torch.float32, device=eng.device)
         ws["arange_r"] = torch.arange(Mr, dtype=torch.int64, device=eng.device).view(B, R)
     ops.build_key_bias(tmask, imask, ws["kb"], ws["row_valid"], m3p_prefix=True)
+    if save and eng.dp is not None and eng.dp.rows_mode():
+        eng.dp.plan_rows(ids, int(getattr(cfg, "pad_index", 1)))
     feats2 = feats.view(Mr, -1)
     locs2 = locs.view(Mr, -1)
     if bf:
@@ -169,6 +171,7 @@ def backward(eng, dl, sv):
                        pad_id=int(getattr(cfg, "pad_index", 1)), dout_map=rowmap(T, R, S), pos_mode=1, pos_base=R)
     if rows_mode:
         eng.dp.add_rows(sv["ids"], de.view(B, S, d)[:, R:, :].reshape(B * T, d))
+        eng.dp.rows_ready(eng)
     else:
         eng.mark_word_rows(sv["ids"])
     # region rows: positions 0..R-1

@@ -39,6 +39,9 @@ class GradExchange:
         self.bucket_layers = int(os.environ.get("CLG_DP_BUCKET_LAYERS", "4"))
         self.scale_after_exchange = 1.0   # 1/world when the optimiser cannot fold the average into its gradient read
         self.trace = None                 # list -> (name, CUDA event) marks of the exchange phases (bench.py --phases)
+        self.plan = None                  # forward-time part of the row exchange (plan_rows)
+        self.row_work = None              # (async all-gather handle, gathered rows, plan) launched by rows_ready
+        self.plan_enabled = os.environ.get("CLG_DP_PLAN", "1") != "0"
 
     def _mark(self, name: str):
         if self.trace is not None and torch.cuda.is_available():
@@ -86,6 +89,60 @@ class GradExchange:
             self._mark("rows_gathered")
         reduce_rows(ids, rows)
         self._mark("rows_reduced")
+
+    # -- the id-only half of the row exchange, done at FORWARD time -------------------------------------------------
+    def plan_rows(self, ids: torch.Tensor, pad_id: int):
+        """Everything of the word-row exchange that depends on the token ids alone - the stable sort of this rank's ids,
+        which copy of a duplicated id carries the summed row, the all-gather of the ids and the sort of the gathered list -
+        is computed when the forward starts, so that the exposed tail after the backward is one row reduction, one
+        all-gather of the rows and one more row reduction.  Identical results: the same lists in the same order."""
+        self.plan = None
+        if not (self.plan_enabled and self.enabled and self.world > 1) or self.row_ids:
+            return
+        flat = ids.reshape(-1)
+        n = flat.numel()
+        sorted_ids, order = torch.sort(flat, stable=True)
+        first = torch.ones(n, dtype=torch.bool, device=flat.device)
+        first[1:] = sorted_ids[1:] != sorted_ids[:-1]
+        send = torch.empty_like(flat)           # the run's first member keeps the id, the others (and padding) are renamed
+        send.scatter_(0, order, torch.where(first, sorted_ids, torch.full_like(sorted_ids, pad_id)))
+        all_ids = torch.empty(self.world * n, dtype=flat.dtype, device=flat.device)
+        dist.all_gather_into_tensor(all_ids, send, group=self.group)
+        all_sorted, all_order = torch.sort(all_ids, stable=True)
+        self.plan = dict(n=n, pad=int(pad_id), sorted=sorted_ids, order=order, scratch=torch.empty_like(flat), all_ids=all_ids,
+                         all_sorted=all_sorted, all_order=all_order)
+
+    def rows_ready(self, engine):
+        """backward: the word-gradient rows of this step exist (add_rows was just called).  With a forward-time plan the local
+        pre-reduction and the all-gather of the rows start NOW, overlapping the rest of the backward (the region half of the
+        embedding backward); after_backward only waits for it."""
+        plan = self.plan
+        self.plan = None
+        if plan is None or not self.enabled or self.world == 1 or len(self.row_ids) != 1 or self.row_ids[0].numel() != plan["n"]:
+            return
+        from . import ops
+        rows = self.row_vals[0]
+        if not rows.is_contiguous():
+            rows = rows.contiguous()
+        self.row_ids, self.row_vals = [], []
+        ops.segment_sum_rows(rows, plan["order"], plan["sorted"], None, plan["pad"], ids_out=plan["scratch"])
+        self._mark("rows_prereduced")
+        all_rows = torch.empty((self.world * rows.shape[0], rows.shape[1]), dtype=rows.dtype, device=rows.device)
+        h = dist.all_gather_into_tensor(all_rows.view(-1), rows.reshape(-1), group=self.group, async_op=True)
+        self.row_work = (h, all_rows, rows, plan)
+
+    def finish_rows(self, engine) -> bool:
+        if self.row_work is None:
+            return False
+        from . import ops
+        h, all_rows, _rows, plan = self.row_work
+        self.row_work = None
+        h.wait()
+        self._mark("rows_gathered")
+        ops.segment_sum_rows(all_rows, plan["all_order"], plan["all_sorted"], engine.grad_view(engine.word_table_param()), plan["pad"])
+        engine.mark_word_rows(plan["all_ids"])
+        self._mark("rows_reduced")
+        return True
 
     def rows_mode(self) -> bool:
         """True: the engine must not scatter its word-table gradient itself but hand the rows to add_rows()"""
@@ -154,7 +211,8 @@ class GradExchange:
             cur = max(cur, b)
         if cur < engine.total:
             self.reduce_range(engine.g_flat, cur, engine.total)
-        self.exchange_rows_deterministic(engine.reduce_word_rows, engine.prereduce_word_rows)
+        if not self.finish_rows(engine):
+            self.exchange_rows_deterministic(engine.reduce_word_rows, engine.prereduce_word_rows)
         self.finish()
         self._mark("allreduce_done")
         if self.scale_after_exchange != 1.0:

@@ -82,6 +82,31 @@ def _worker(rank, world, port, out):
         all_t2 = [torch.zeros_like(t2) for _ in range(world)]
         dist.all_gather(all_t2, t2)
         ok = ok and all(torch.equal(all_t2[0], t) for t in all_t2)       # replicas bit-identical
+        # forward-time plan of the row exchange (plan_rows): duplicated ids keep one carrier row per rank, the padding id
+        # is never sent, and the gathered + sorted list reduces to the same table
+        PAD = 1
+        ids3 = torch.randint(0, 6, (NTOK,)); rows3 = torch.randn(NTOK, D)        # many duplicates, some padding ids
+        ex.plan_rows(ids3, PAD)
+        plan = ex.plan
+        local = torch.zeros(V, D).index_add_(0, ids3, rows3)
+        send = plan["all_ids"].view(world, NTOK)[rank]
+        keep = send != PAD
+        ok = ok and bool((send[keep] == ids3[keep]).all()) and send[keep].unique().numel() == int(keep.sum())
+        ok = ok and set(send[keep].tolist()) == set(ids3[ids3 != PAD].tolist())
+        carried = torch.where(keep[:, None], local[ids3], torch.zeros_like(rows3))      # what the local pre-reduction leaves
+        gathered = [torch.zeros_like(carried) for _ in range(world)]
+        dist.all_gather(gathered, carried)
+        all_rows = torch.cat(gathered)
+        t3 = torch.zeros(V, D)
+        so, od = plan["all_sorted"], plan["all_order"]
+        live = so != PAD
+        t3.index_add_(0, so[live], all_rows[od[live]])
+        all_i3 = [torch.zeros_like(ids3) for _ in range(world)]; all_r3 = [torch.zeros_like(rows3) for _ in range(world)]
+        dist.all_gather(all_i3, ids3); dist.all_gather(all_r3, rows3)
+        ref3 = torch.zeros(V, D)
+        for i, r in zip(all_i3, all_r3):
+            ref3.index_add_(0, i[i != PAD], r[i != PAD])
+        ok = ok and torch.allclose(t3, ref3, atol=1e-5) and bool(torch.equal(so, torch.sort(plan["all_ids"], stable=True).values))
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

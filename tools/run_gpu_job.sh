@@ -29,8 +29,8 @@ case "$1" in
     launch_list eval_uc2 r02_eval_uc2_c
     ;;
   ncu1)
-    python -m pytest tests/test_gemm_fast_gpu.py tests/test_model_gpu.py -m gpu -q -x 2>&1 | tail -3
-    python bench.py --config eval_uc2 --no-cpu-baseline --steps 8 > $out/bench_n1_eval_uc2.log 2>&1; tail -c 1200 $out/bench_n1_eval_uc2.log | grep -o '"value": [0-9.]*\|"ms_per_step": [0-9.]*' | head -2 | tr '\n' ' '; echo
+    python -m pytest tests/test_ops_gpu.py tests/test_m3p_gpu.py tests/test_model_gpu.py tests/test_layerwise_gpu.py -m gpu -q -x 2>&1 | tail -3
+    for c in uc2_train eval_uc2 m3p_train; do python bench.py --config $c --no-cpu-baseline --steps 8 > $out/bench_n1_$c.log 2>&1; tail -c 1500 $out/bench_n1_$c.log | grep -o '"value": [0-9.]*\|"ms_per_step": [0-9.]*' | head -2 | tr '\n' ' '; echo $c; done
     python tools/profile_step.py > $out/prof_plain_ncu1.log 2>&1 || { echo "plain profile_step failed"; exit 1; }
     cap() {  # $1 = tag, $2 = CONFIG, $3 = demangled-name regex, $4 = skip
       CONFIG=$2 ncu --profile-from-start off --set full --import-source on --clock-control none --kernel-name-base demangled -k "regex:$3" -s $4 -c 1 \
@@ -41,10 +41,12 @@ case "$1" in
       python tools/ncu_source_top.py /tmp/src_$1.csv 45 > $out/r02_ncu_stalls_$1.txt 2>/dev/null
       head -4 $out/r02_ncu_summary_$1.txt
     }
-    cap gemm_wgrad uc2_train 'gemm_tc_kernel<256, 0, 0, 2, 0>' 6
-    cap gemm_gelu_pair uc2_train 'gemm_tc_kernel<256, 1, 1, 2, 3>' 4
-    cap gemm_mul_aux uc2_train 'gemm_tc_kernel<256, 1, 0, 2, 4>' 4
-    cap gemm_resid_ffn2 uc2_train 'gemm_tc_kernel<256, 1, 1, 2, 2>' 9
+    cap gemm_wgrad uc2_train 'gemm_tc_kernel<.int.256, .bool.0, .bool.0, .int.2, .int.0>' 6
+    cap gemm_gelu_pair uc2_train 'gemm_tc_kernel<.int.256, .bool.1, .bool.1, .int.2, .int.3>' 4
+    cap gemm_mul_aux uc2_train 'gemm_tc_kernel<.int.256, .bool.1, .bool.0, .int.2, .int.4>' 4
+    cap gemm_resid_ffn2 uc2_train 'gemm_tc_kernel<.int.256, .bool.1, .bool.1, .int.2, .int.2>' 9
     cap attn_wide eval_uc2 'attn_pipe_fwd_wide_kernel' 4
+    cap attn_bwd uc2_train 'attn_pipe_bwd_kernel' 3
+    launch_list eval_uc2 r02_eval_uc2_d
     ;;
 esac
