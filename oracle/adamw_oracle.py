@@ -1,12 +1,14 @@
 """Oracle: optimiser step of the fine-tune loop.  TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED: the algorithm is `AdamW` / `WarmupLinearSchedule` of the un-vendored pip
-dependency pytorch-transformers (>=1.1.0, volta/requirements.txt:L51), absent from
-/root/reference.  Restated from its published algorithm and anchored on
-the reference's call sites: train_task.py:L249-276 (groups, AdamW ctor, schedule) and L326-338
-(clip_grad_norm_(1.0) -> optimizer.step() -> scheduler.step() -> zero_grad()).
-Cross-checked in tests against torch.optim.Adam on the case where they coincide
-(weight_decay = 0, eps -> 0 difference bounded).
+The fine-tune loop takes `AdamW` / `WarmupLinearSchedule` from the un-vendored pip dependency
+pytorch-transformers (>=1.1.0, volta/requirements.txt:L51; call sites train_task.py:L249-276 groups /
+ctor / schedule, L326-338 clip_grad_norm_(1.0) -> optimizer.step() -> scheduler.step() -> zero_grad()).
+PINNED (round 2): the reference tree vendors that optimiser's step body verbatim at
+features_extraction/mmf/mmf/modules/optimizers.py:L15-84 (the HuggingFace AdamW = pytorch-transformers
+1.x algorithm: eps before the bias correction, decoupled decay after the update); oracle/make_golden_adamw.py
+executes it unmodified and tests/test_oracle_golden.py::test_adamw_oracle_and_module_match_reference_tree_step
+requires bit-equal trajectories (tests/golden/adamw_ref_step.npz).  The schedule is pinned against
+transformers.get_linear_schedule_with_warmup (the same lambda, installed package).
 """
 from __future__ import annotations
 

@@ -230,3 +230,55 @@ def test_torch_gpu_baseline_matches_oracle(case):
         f = tb.uc2_forward if meta["family"] == "uc2" else tb.m3p_forward
         lg = f(fp, cfg, *_args(b))
     assert _rel(lg, g["logits_fp32"]) <= 1e-5
+
+
+def _adamw_cases():
+    g = np.load(os.path.join(GOLDEN, "adamw_ref_step.npz"), allow_pickle=False)
+    names = sorted({k.split("::")[0] for k in g.files if "::" in k})
+    return g, names
+
+
+def test_adamw_oracle_and_module_match_reference_tree_step():
+    """AdamW pinned to code inside the reference tree: the HuggingFace / pytorch-transformers step body vendored at
+    features_extraction/mmf/mmf/modules/optimizers.py:L15-84, executed unmodified by oracle/make_golden_adamw.py.
+    Both the oracle restatement and clg_vqa_b200.optim.AdamW (per-parameter path, CPU) reproduce its trajectories."""
+    from clg_vqa_b200 import optim
+    from oracle import adamw_oracle
+    g, names = _adamw_cases()
+    assert len(names) >= 4
+    for name in names:
+        lr, b1, b2, eps, wd, cb = [float(x) for x in g[name + "::hyper"]]
+        grads = torch.from_numpy(g[name + "::grads"])
+        want = torch.from_numpy(g[name + "::params"])
+        # oracle
+        p = torch.from_numpy(g[name + "::p0"]).clone()
+        m = torch.zeros_like(p); v = torch.zeros_like(p)
+        for t in range(grads.shape[0]):
+            adamw_oracle.adamw_step(p, grads[t], m, v, t + 1, lr, b1, b2, eps, wd, bool(cb))
+            assert torch.equal(p, want[t]), (name, t, float((p - want[t]).abs().max()))
+        assert torch.equal(m, torch.from_numpy(g[name + "::exp_avg"])) and torch.equal(v, torch.from_numpy(g[name + "::exp_avg_sq"]))
+        # module (same call sequence as train_task.py:L326-338 minus the clip)
+        q = torch.nn.Parameter(torch.from_numpy(g[name + "::p0"]).clone())
+        opt = optim.AdamW([q], lr=lr, betas=(b1, b2), eps=eps, weight_decay=wd, correct_bias=bool(cb))
+        for t in range(grads.shape[0]):
+            q.grad = grads[t].clone()
+            opt.step()
+            assert torch.equal(q.detach(), want[t]), (name, t)
+
+
+def test_warmup_linear_schedule_matches_transformers():
+    """WarmupLinearSchedule (pytorch-transformers 1.x; call site train_task.py:L271-274) against its direct successor in the
+    installed transformers package, get_linear_schedule_with_warmup - the same lambda."""
+    from transformers.optimization import get_linear_schedule_with_warmup
+    from clg_vqa_b200 import optim
+    from oracle import adamw_oracle
+    for warm, total in ((0, 50), (10, 50), (100, 1000), (7, 7)):
+        pa = torch.nn.Parameter(torch.zeros(1)); pb = torch.nn.Parameter(torch.zeros(1))
+        oa = torch.optim.SGD([pa], lr=4e-5); ob = torch.optim.SGD([pb], lr=4e-5)
+        sa = optim.WarmupLinearSchedule(oa, warmup_steps=warm, t_total=total)
+        sb = get_linear_schedule_with_warmup(ob, warm, total)
+        for step in range(min(total + 5, 120)):
+            la, lb = oa.param_groups[0]["lr"], ob.param_groups[0]["lr"]
+            assert abs(la - lb) <= 1e-12 * max(1.0, lb), (warm, total, step, la, lb)
+            assert abs(adamw_oracle.warmup_linear_lr(4e-5, step, warm, total) - lb) <= 1e-12
+            oa.step(); ob.step(); sa.step(); sb.step()
