@@ -173,6 +173,33 @@ segment_sum_rows_kernel(float* __restrict__ rows, int64_t ld_rows, const int64_t
     for (int k = k0 + 1 + threadIdx.x; k < k1; k += 256) ids_out[order[k]] = pad_id;
 }
 
+// mode 0 after the local pre-reduction: an id occurs at most once per rank, so runs are at most world-size long and a
+// whole CTA per list position is mostly launch overhead (82 k CTAs at 8 ranks).  Here a WARP owns a list position; the
+// head of a run sums its members in list order with the row spread over the lanes (float4 per lane and 128-column step).
+// Same order on every rank: deterministic and replica-identical like the CTA version.
+__global__ void __launch_bounds__(256)
+segment_sum_rows_warp_kernel(const float* __restrict__ rows, int64_t ld_rows, const int64_t* __restrict__ order,
+                             const int64_t* __restrict__ sorted_ids, int n, float* __restrict__ table, int N, int64_t pad_id) {
+  const int k0 = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k0 >= n) return;
+  const int64_t id = sorted_ids[k0];
+  if (id == pad_id || (k0 > 0 && sorted_ids[k0 - 1] == id)) return;      // not the head of a run
+  int k1 = k0 + 1;
+  while (k1 < n && sorted_ids[k1] == id) ++k1;
+  float* dst = table + id * N;
+  for (int c = lane * 4; c < N; c += 128) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = k0; k < k1; ++k) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(rows + order[k] * ld_rows + c));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float4 d = *reinterpret_cast<float4*>(dst + c);
+    d.x += acc.x; d.y += acc.y; d.z += acc.z; d.w += acc.w;
+    *reinterpret_cast<float4*>(dst + c) = d;
+  }
+}
+
 }  // namespace clg
 
 extern "C" int clg_segment_sum_rows(float* rows, int64_t ld_rows, const int64_t* order, const int64_t* sorted_ids, int32_t n,
@@ -183,6 +210,13 @@ extern "C" int clg_segment_sum_rows(float* rows, int64_t ld_rows, const int64_t*
   int st = require_sm100();
   if (st != CLG_OK) return st;
   if (n == 0) return CLG_OK;
+  // mode 0 with 16 B-granular rows: warp per list position (runs are short after the local pre-reduction; a long run is
+  // still summed correctly, only serially).  The summation order differs from the CTA kernel's 8-way split, so the
+  // choice depends on the arguments alone - never on the data - and every rank makes the same one.
+  if (mode == 0 && (N % 4) == 0 && (ld_rows % 4) == 0 && ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(table)) & 15) == 0) {
+    segment_sum_rows_warp_kernel<<<(n + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, ld_rows, order, sorted_ids, n, table, N, pad_id);
+    return check_launch("segment_sum_rows_warp_kernel");
+  }
   segment_sum_rows_kernel<<<n, 256, 8 * N * sizeof(float), static_cast<cudaStream_t>(stream)>>>(rows, ld_rows, order, sorted_ids, n, table,
                                                                                               N, pad_id, mode, ids_out);
   return check_launch("segment_sum_rows_kernel");

@@ -342,7 +342,8 @@ typedef struct {
                                         gradient): only the decoupled decay p -= lr*wd*p is applied - bit-identical to the
                                         dense update, 8 instead of 28 bytes of HBM traffic per parameter (the word-embedding
                                         rows a batch never touches); when lr*wd < 2^-25 that decay rounds to p itself and
-                                        the block is not touched at all */
+                                        the block is not touched at all (its shadow, if any, must already hold bf16(p*mask):
+                                        clg_cast_shadow after every out-of-band change of p) */
 } clgAdamWParams;
 
 /* out[0] += sum g^2 (two deterministic passes).  hot (optional, [n/256] bytes): hot[b] = 1 for every 256-element block

@@ -113,7 +113,9 @@ def test_adamw_cold_blocks_bit_identical_to_dense(wd):
     state = {}
     for mode in ("dense", "hot", "hot+zero", "dense+zero"):
         p = p0.clone(); m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV)
-        shadow = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
+        # the kernel's precondition (Engine._refresh keeps it): the shadow already holds bf16(p) - blocks the step does not
+        # touch (cold, decay below half an ulp) keep their shadow as it is
+        shadow = p0.to(torch.bfloat16)
         hot = torch.zeros(n // 256, device=DEV, dtype=torch.uint8)
         partials = torch.zeros(1024, device=DEV); ss = torch.zeros(1, device=DEV)
         gen = torch.Generator(device="cpu").manual_seed(11)
