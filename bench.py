@@ -487,10 +487,23 @@ def run_ours(args, spec):
         from clg_vqa_b200.data import DevicePrefetcher
         pf = DevicePrefetcher((host[i % NB] for i in range(n)), dev, reuse=pf_state.get("pf"))
         pf_state["pf"] = pf
-        for batch in pf:
+        # every step's loss is copied to pinned host memory on the compute stream and read by the host ONE step later
+        # (the logger's float(loss) of train_task.py:L340, without stalling the launch queue); the last one before the end
+        pin = pf_state.setdefault("pin", torch.empty(4096, dtype=torch.float32).pin_memory())
+        prev = None
+        for i, batch in enumerate(pf):
             out, _ = step(batch)
             if train:
-                losses.append(float(out.detach()))   # D2H read of the step's loss
+                pin[i % 4096].copy_(out.detach(), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if prev is not None:
+                    prev[0].synchronize()
+                    losses.append(float(pin[prev[1] % 4096]))          # D2H read of the previous step's loss
+                prev = (ev, i)
+        if prev is not None:
+            prev[0].synchronize()
+            losses.append(float(pin[prev[1] % 4096]))
 
     # warm-up (also builds arenas / workspaces)
     loop_resident(max(3, args.warmup))

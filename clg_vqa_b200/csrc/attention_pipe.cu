@@ -69,8 +69,7 @@ static constexpr float LOG2E = 1.4426950408889634f;
 static constexpr float LN2 = 0.6931471805599453f;
 
 // barrier slots (8 B each) inside the first KiB of shared memory
-enum { PB_FULL = 0, PB_EMPTY = 4, PB_SRDY = 8, PB_PRDY = 11, PB_ORDY = 14, PB_TFREE = 17, PB_SFREE = 20, PB_COUNT = 23,
-       PB_FULLV = 28, PB_QKFREE = 32 };      // forward: V has its own full barrier, Q | K are released as soon as S = Q K^T is done
+enum { PB_FULL = 0, PB_EMPTY = 4, PB_SRDY = 8, PB_PRDY = 11, PB_ORDY = 14, PB_TFREE = 17, PB_SFREE = 20, PB_COUNT = 23 };
 
 // lane 0's probe result for the whole (converged) warp
 __device__ __forceinline__ bool warp_probe(uint32_t bar, uint32_t parity) {
@@ -84,7 +83,7 @@ __device__ __forceinline__ bool warp_probe(uint32_t bar, uint32_t parity) {
 // TMEM: group g owns TG columns: S in [0, NP), O in [TO, TO + 64) - separate, so S of the group's next item is
 // computed while the current item's P V product and output are still in flight (NG = 3: TG = 160, TO = 96)
 // ------------------------------------------------------------------------------------------------
-template <int NCH, int NG, bool TRACE>      // NP = 16 * NCH keys; NG softmax groups (3 when 3 x (S + O) columns fit in TMEM)
+template <int NCH, int NG>      // NP = 16 * NCH keys; NG softmax groups (3 when 3 x (S + O) columns fit in TMEM)
 __global__ void __launch_bounds__(64 + 128 * NG, 1)
 attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_ctx, const AttnPipeArgs a) {
   constexpr int NP = NCH * 16;
@@ -109,9 +108,7 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_ctx);
-    for (int s = 0; s < 4; ++s) {
-      mbar_init(bar(PB_FULL + s), 1); mbar_init(bar(PB_EMPTY + s), 1); mbar_init(bar(PB_FULLV + s), 1); mbar_init(bar(PB_QKFREE + s), 1);
-    }
+    for (int s = 0; s < 4; ++s) { mbar_init(bar(PB_FULL + s), 1); mbar_init(bar(PB_EMPTY + s), 1); }
     for (int g = 0; g < NG; ++g) {
       mbar_init(bar(PB_SRDY + g), 1); mbar_init(bar(PB_PRDY + g), 4); mbar_init(bar(PB_ORDY + g), 1); mbar_init(bar(PB_TFREE + g), 4);
       mbar_init(bar(PB_SFREE + g), 4);
@@ -128,46 +125,21 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   const int n_it = ((int)blockIdx.x < a.items) ? (a.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0) {
-    // ---------------- TMA producer: Q | K of an item are re-loadable as soon as its S = Q K^T has completed, V only after
-    // its P V - two independent streams, so the Q / K loads run a full round of items ahead and S of the next item is
-    // in TMEM before the softmax group asks for it (the load latency was 29 % of the per-item chain) ----------------
-    int nqk = 0, nv = 0;
-    while (nqk < n_it || nv < n_it) {
-      if (nqk < n_it) {
-        const int s = nqk % NST;
-        if (warp_probe(bar(PB_QKFREE + s), ((nqk / NST) & 1) ^ 1u)) {
-          const int w = (int)blockIdx.x + nqk * (int)gridDim.x;
-          const int b = w / H, h = w % H;
-          const int row0 = a.cu ? __ldg(a.cu + b) : b * S;
-          if (elect_one()) {
-            ATR(0, nqk, 0);
-            const uint32_t st = sStage + (uint32_t)s * 3u * TN;
-            mbar_expect_tx(bar(PB_FULL + s), 2u * TN);
-            tma_load_2d(st, &tm_qkv, bar(PB_FULL + s), h * PD, row0);
-            tma_load_2d(st + TN, &tm_qkv, bar(PB_FULL + s), H * PD + h * PD, row0);
-          }
-          __syncwarp();
-          ++nqk;
-          continue;
-        }
+    // ---------------- TMA producer ----------------
+    for (int it = 0; it < n_it; ++it) {
+      const int w = (int)blockIdx.x + it * (int)gridDim.x;
+      const int s = it % NST;
+      mbar_wait(bar(PB_EMPTY + s), ((it / NST) & 1) ^ 1u);
+      const int b = w / H, h = w % H;
+      const int row0 = a.cu ? __ldg(a.cu + b) : b * S;
+      if (elect_one()) {
+        const uint32_t st = sStage + (uint32_t)s * 3u * TN;
+        mbar_expect_tx(bar(PB_FULL + s), 3u * TN);
+        tma_load_2d(st, &tm_qkv, bar(PB_FULL + s), h * PD, row0);
+        tma_load_2d(st + TN, &tm_qkv, bar(PB_FULL + s), H * PD + h * PD, row0);
+        tma_load_2d(st + 2 * TN, &tm_qkv, bar(PB_FULL + s), 2 * H * PD + h * PD, row0);
       }
-      if (nv < n_it) {
-        const int s = nv % NST;
-        if (warp_probe(bar(PB_EMPTY + s), ((nv / NST) & 1) ^ 1u)) {
-          const int w = (int)blockIdx.x + nv * (int)gridDim.x;
-          const int b = w / H, h = w % H;
-          const int row0 = a.cu ? __ldg(a.cu + b) : b * S;
-          if (elect_one()) {
-            const uint32_t st = sStage + (uint32_t)s * 3u * TN;
-            mbar_expect_tx(bar(PB_FULLV + s), TN);
-            tma_load_2d(st + 2 * TN, &tm_qkv, bar(PB_FULLV + s), 2 * H * PD + h * PD, row0);
-          }
-          __syncwarp();
-          ++nv;
-          continue;
-        }
-      }
-      __nanosleep(128);        // nothing to issue: do not compete for issue slots with the softmax warps of this sub-partition
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer: issues whichever of {S(next), PV(next)} has its operands ready, so the two
@@ -183,8 +155,6 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         for (int k = 0; k < PD / 16; ++k)
           umma_bf16(tS, umma_desc(st + k * 32, 16, 1024), umma_desc(st + TN + k * 32, 16, 1024), idesc, k > 0);
         umma_commit(bar(PB_SRDY + g));
-        umma_commit(bar(PB_QKFREE + s));         // Q, K of this stage are consumed
-        ATR(1, it, 0);
       }
       __syncwarp();
     };
@@ -200,8 +170,7 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         for (int k = 0; k < NP / 16; ++k)
           umma_bf16(tO, umma_desc(sP + (k >> 2) * TN + (k & 3) * 32, 16, 1024), umma_desc(sV + k * 2048, 8192, 1024), idesc, k > 0);
         umma_commit(bar(PB_ORDY + g));
-        umma_commit(bar(PB_EMPTY + s));          // V of this stage is consumed
-        ATR(1, it, 1);
+        umma_commit(bar(PB_EMPTY + s));          // Q, K, V of this stage are consumed
       }
       __syncwarp();
     };
@@ -209,8 +178,7 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     while (npv < n_it) {
       if (npv < ns) {
         const int g = npv % NG, u = npv / NG;
-        if (warp_probe(bar(PB_PRDY + g), u & 1) && warp_probe(bar(PB_TFREE + g), (u & 1) ^ 1u) &&
-            warp_probe(bar(PB_FULLV + npv % NST), (npv / NST) & 1)) { issue_pv(npv); ++npv; continue; }
+        if (warp_probe(bar(PB_PRDY + g), u & 1) && warp_probe(bar(PB_TFREE + g), (u & 1) ^ 1u)) { issue_pv(npv); ++npv; continue; }
       }
       if (ns < n_it) {
         const int s = ns % NST, g = ns % NG, u = ns / NG;
@@ -255,14 +223,12 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       const bool warp_live = wq * 32 < Sb;
       const float kbv = kb_next;
       kb_next = load_kb(it + NG);                  // in flight during this item
-      if (tg == 0) ATR(2 + g, it, 0);
       if (tg == 0) bulk_wait_read<0>();            // the previous TMA store has read the O staging tile
       named_bar(1 + g, 128);                       // every thread of the group is done with the previous item's key bias
       if (tg < NP) kb[tg] = kbv;
       named_bar(1 + g, 128);
       mbar_wait(bar(PB_SRDY + g), u & 1);
       __syncwarp();
-      if (tg == 0) ATR(2 + g, it, 1);
       tcgen05_fence_after();
       float m = -INFINITY, sum = 0.f;
       if (warp_live) {
@@ -275,8 +241,7 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         // the scores are in registers: the S columns may be overwritten by the group's next item
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(PB_SFREE + g));
-        if (tg == 0) ATR(2 + g, it, 2);
+        if (lane == 0) mbar_arrive_relaxed(bar(PB_SFREE + g));
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};       // four independent chains
 #pragma unroll
         for (int j = 0; j < NP; ++j) { ex[j] = fmaf(ex[j], scale2, kb[j]); m4[j & 3] = fmaxf(m4[j & 3], ex[j]); }
@@ -305,7 +270,7 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           }
         }
       } else {
-        if (lane == 0) mbar_arrive(bar(PB_SFREE + g));
+        if (lane == 0) mbar_arrive_relaxed(bar(PB_SFREE + g));
         if (in_tile)
           for (int j = 0; j < NP; j += 8)
             *reinterpret_cast<uint4*>(gP + (j >> 6) * TN + psw_off(row, j & 63)) = make_uint4(0, 0, 0, 0);
@@ -314,11 +279,9 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(PB_PRDY + g));
-      if (tg == 0) ATR(2 + g, it, 5);
       if (warp_live && valid && a.lse) a.lse[((int64_t)b * H + h) * S + row] = (m + __log2f(sum)) * LN2;
       mbar_wait(bar(PB_ORDY + g), u & 1);
       __syncwarp();
-      if (tg == 0) ATR(2 + g, it, 6);
       tcgen05_fence_after();
       if (warp_live) {
         float o[64];
@@ -336,7 +299,7 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(PB_TFREE + g));
+      if (lane == 0) mbar_arrive_relaxed(bar(PB_TFREE + g));
       if (!a.cu) {
         fence_proxy_async();
         named_bar(1 + g, 128);
@@ -351,7 +314,6 @@ attn_pipe_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
               *reinterpret_cast<const uint4*>(gO + psw_off(r, 8 * j));
         }
       }
-      if (tg == 0) ATR(2 + g, it, 7);
     }
     if (tg == 0) bulk_wait_all();
   }
@@ -643,7 +605,7 @@ attn_pipe_fwd_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       tcgen05_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(bar(PB_SFREE + g)); mbar_arrive(bar(PB_PRDY + g)); }
+      if (lane == 0) { mbar_arrive_relaxed(bar(PB_SFREE + g)); mbar_arrive(bar(PB_PRDY + g)); }
       if (tg == 0) ATR(2 + g, k, 4);
       if (warp_live && valid && a.lse) a.lse[((int64_t)b * H + h) * S + q] = (m + __log2f(sum)) * LN2;
       mbar_wait(bar(PB_ORDY + g), k & 1);           // O in TMEM; the P blocks are free again
@@ -666,7 +628,7 @@ attn_pipe_fwd_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(PB_TFREE + g));
+      if (lane == 0) mbar_arrive_relaxed(bar(PB_TFREE + g));
       // coalesced copy-out of the staged tile: 8 lanes per 128 B row
       named_bar(1 + g, 128);
       const int nrows = min(128, Sb - ut * 128);
@@ -1063,7 +1025,7 @@ attn_pipe_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(PB_TFREE + g));
+      if (lane == 0) mbar_arrive_relaxed(bar(PB_TFREE + g));
       if (!a.cu) {
         fence_proxy_async();
         named_bar(1 + g, 128);
@@ -1121,17 +1083,10 @@ static int launch_pipe_fwd(const CUtensorMap& tq, const CUtensorMap& tc, const A
   constexpr int NG = NCH <= 6 ? 3 : 2;
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
-  std::call_once(once, [] {
-    err = cudaFuncSetAttribute(attn_pipe_fwd_kernel<NCH, NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_MAX);
-    if (err == cudaSuccess && NCH == 5) err = cudaFuncSetAttribute(attn_pipe_fwd_kernel<NCH, NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_MAX);
-  });
+  std::call_once(once, [] { err = cudaFuncSetAttribute(attn_pipe_fwd_kernel<NCH, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_MAX); });
   CLG_CUDA_OK(err, "cudaFuncSetAttribute(attn_pipe_fwd)");
   const int grid = a.items < num_sms() ? a.items : num_sms();
-  if (NCH == 5 && a.trace) {       // debug timeline (tools/attn_trace.py): the instrumented instantiation exists for S in (64, 80] only
-    CLG_CUDA_OK(launch_pdl(attn_pipe_fwd_kernel<NCH == 5 ? 5 : NCH, NG, NCH == 5>, dim3(grid), dim3(64 + 128 * NG), (size_t)smem, stream, tq, tc, a), "launch(attn_pipe_fwd)");
-    return check_launch("attn_pipe_fwd_kernel");
-  }
-  CLG_CUDA_OK(launch_pdl(attn_pipe_fwd_kernel<NCH, NG, false>, dim3(grid), dim3(64 + 128 * NG), (size_t)smem, stream, tq, tc, a), "launch(attn_pipe_fwd)");
+  CLG_CUDA_OK(launch_pdl(attn_pipe_fwd_kernel<NCH, NG>, dim3(grid), dim3(64 + 128 * NG), (size_t)smem, stream, tq, tc, a), "launch(attn_pipe_fwd)");
   return check_launch("attn_pipe_fwd_kernel");
 }
 
@@ -1209,7 +1164,6 @@ int attention_pipe_fwd(const clgAttentionFwdParams& p, cudaStream_t stream) {
   a.scale = p.scale; a.key_bias = p.key_bias; a.lse = p.lse;
   a.drop = make_drop(p.dropout);
   a.cu = p.cu_rows; a.out = (bf16*)p.ctx; a.ld_out = p.ld_ctx;
-  a.trace = g_attn_trace;
   const int smem = fwd_pipe_smem(NP, nst, ng);
   switch (NP / 16) {
     case 1: return launch_pipe_fwd<1>(tq, tc, a, smem, stream);

@@ -280,7 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) { if (MC == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
+        if (lane == 0) { if (MC == 2) mbar_arrive_cluster_relaxed(mapa_shared(tempty_bar(as), 0)); else mbar_arrive_relaxed(tempty_bar(as)); }   // TMEM-only hand-off
       }
     } else {
       // fast forms (splits == 1): this warp owns columns [half*BN/2, (half+1)*BN/2) of its 32-row slab and walks
@@ -327,7 +327,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) { if (MC == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as)); }
+        if (lane == 0) { if (MC == 2) mbar_arrive_cluster_relaxed(mapa_shared(tempty_bar(as), 0)); else mbar_arrive_relaxed(tempty_bar(as)); }   // TMEM-only hand-off
       }
       if (lane == 0) bulk_wait_all();      // shared-memory boxes must outlive their TMA stores
     }

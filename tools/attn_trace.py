@@ -1,4 +1,4 @@
-"""Timeline of the pipelined attention forward (CTA 0, first 16 items) from the kernel's clock64 stamps
+"""Timeline of the pipelined attention forward for 128 < S <= 160 (CTA 0, first 16 units) from the kernel's clock64 stamps
 (clg_debug_attn_trace): where the per-item latency chain spends its cycles.   python tools/attn_trace.py [B] [S]"""
 import ctypes
 import os
@@ -9,7 +9,7 @@ import torch
 from clg_vqa_b200 import _lib as L, ops
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-S = int(sys.argv[2]) if len(sys.argv) > 2 else 76
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 140       # the instrumented instantiation is the S in (128, 160] forward
 H, D = 12, 768
 dev = "cuda"
 torch.manual_seed(0)

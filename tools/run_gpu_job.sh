@@ -49,4 +49,9 @@ case "$1" in
     cap attn_bwd uc2_train 'attn_pipe_bwd_kernel' 3
     launch_list eval_uc2 r02_eval_uc2_d
     ;;
+  relax1)
+    python -m pytest tests/test_ops_gpu.py tests/test_ops2_gpu.py tests/test_gemm_fast_gpu.py tests/test_model_gpu.py tests/test_m3p_gpu.py -m gpu -q -x 2>&1 | tail -3
+    for c in uc2_train eval_uc2 m3p_train; do python bench.py --config $c --no-cpu-baseline --steps 10 > $out/bench_r1_$c.log 2>&1; tail -c 1500 $out/bench_r1_$c.log | grep -o '"value": [0-9.]*\|"ms_per_step": [0-9.]*' | head -2 | tr '\n' ' '; echo $c; done
+    launch_list uc2_train r02_uc2_train_b
+    ;;
 esac
