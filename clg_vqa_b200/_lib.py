@@ -130,6 +130,14 @@ class GqaLossParams(C.Structure):
     ]
 
 
+class ColsumParams(C.Structure):          # clg_colsum's arguments as a struct (launch plans)
+    _fields_ = [("x", c_vp), ("out", c_vp), ("ld", c_i64), ("dtype", c_i32), ("M", c_i32), ("N", c_i32), ("_pad", c_i32)]
+
+
+class PlanEntry(C.Structure):             # one launch of a recorded plan (clg_run_plan)
+    _fields_ = [("op", c_i32), ("off", c_i32), ("rows_off", c_i32 * 2), ("seed_off", c_i32 * 2)]
+
+
 class TensorMeta(C.Structure):
     _fields_ = [("lr", c_f32), ("wd", c_f32), ("shadow_off", c_i64), ("mask_off", c_i64),
                 ("start", c_i64), ("numel", c_i64)]
@@ -159,6 +167,8 @@ _SIZEOF_CHECKS = {
     "clg_sizeof_adamw_params": AdamWParams,
     "clg_sizeof_tensor_meta": TensorMeta,
     "clg_sizeof_prune_tensor": PruneTensor,
+    "clg_sizeof_plan_entry": PlanEntry,
+    "clg_sizeof_colsum_params": ColsumParams,
 }
 
 # every symbol include/clgvqa.h declares: name -> (restype, argtypes)
@@ -180,6 +190,9 @@ SYMBOLS = {
     "clg_embed_text_bwd": (C.c_int, [C.POINTER(EmbedTextBwdParams), c_vp]),
     "clg_gqa_prior_loss": (C.c_int, [C.POINTER(GqaLossParams), c_vp]),
     "clg_sumsq": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "clg_run_plan": (C.c_int, [c_vp, c_i32, c_vp, c_i32, C.c_uint64, c_vp]),
+    "clg_sizeof_plan_entry": (C.c_size_t, []),
+    "clg_sizeof_colsum_params": (C.c_size_t, []),
     "clg_sumsq_sparse": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "clg_mark_rows": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "clg_adamw_step": (C.c_int, [C.POINTER(AdamWParams), c_vp]),

@@ -128,5 +128,36 @@ size_t clg_sizeof_embed_text_bwd_params(void) { return sizeof(clgEmbedTextBwdPar
 size_t clg_sizeof_gqa_loss_params(void) { return sizeof(clgGqaLossParams); }
 size_t clg_sizeof_adamw_params(void) { return sizeof(clgAdamWParams); }
 size_t clg_sizeof_tensor_meta(void) { return sizeof(clgTensorMeta); }
+size_t clg_sizeof_plan_entry(void) { return sizeof(clgPlanEntry); }
+size_t clg_sizeof_colsum_params(void) { return sizeof(clgColsumParams); }
+
+int clg_run_plan(const clgPlanEntry* entries, int32_t n, void* blob, int32_t rows, uint64_t seed, clgStream_t stream) {
+  if (n < 0 || (n > 0 && (!entries || !blob))) return CLG_ERR_ARG;
+  uint8_t* base = static_cast<uint8_t*>(blob);
+  for (int32_t i = 0; i < n; ++i) {
+    const clgPlanEntry& e = entries[i];
+    uint8_t* p = base + e.off;
+    for (int k = 0; k < 2; ++k) {
+      if (e.rows_off[k] >= 0) memcpy(p + e.rows_off[k], &rows, sizeof(int32_t));
+      if (e.seed_off[k] >= 0) memcpy(p + e.seed_off[k], &seed, sizeof(uint64_t));
+    }
+    int st;
+    switch (e.op) {
+      case CLG_OP_GEMM: st = clg_gemm(reinterpret_cast<const clgGemmParams*>(p), stream); break;
+      case CLG_OP_LN_FWD: st = clg_layernorm_fwd(reinterpret_cast<const clgLayerNormFwdParams*>(p), stream); break;
+      case CLG_OP_LN_BWD: st = clg_layernorm_bwd(reinterpret_cast<const clgLayerNormBwdParams*>(p), stream); break;
+      case CLG_OP_ATTN_FWD: st = clg_attention_fwd(reinterpret_cast<const clgAttentionFwdParams*>(p), stream); break;
+      case CLG_OP_ATTN_BWD: st = clg_attention_bwd(reinterpret_cast<const clgAttentionBwdParams*>(p), stream); break;
+      case CLG_OP_COLSUM: {
+        const clgColsumParams* c = reinterpret_cast<const clgColsumParams*>(p);
+        st = clg_colsum(c->x, c->dtype, c->ld, c->M, c->N, c->out, stream);
+        break;
+      }
+      default: return CLG_ERR_ARG;
+    }
+    if (st != CLG_OK) return st;
+  }
+  return CLG_OK;
+}
 
 }  // extern "C"

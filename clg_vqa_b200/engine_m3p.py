@@ -115,10 +115,12 @@ def forward(eng, ids, feats, locs, task_id, seg, tmask, imask, training, save):
         a = enc.attentions[l]
         lw = ws["layers"][l % nslots]
         eng._probe_inject(l, x, x_lp, B, S, pack)
-        x, x_lp = eng._layer_fwd(lw, x, x_lp, kb, B, S, a.q_lin, a.out_lin, enc.layer_norm1[l], enc.ffns[l].lin1,
-                                 enc.ffns[l].lin2, enc.layer_norm2[l], eps, 0.125, eng._site(2 + 4 * l, p_a, training),
-                                 eng._site(3 + 4 * l, p_h, training), eng._site(4 + 4 * l, p_h, training), bf,
-                                 row_valid=row_valid, rows=rows, cu=cu, save=save)
+        eng._planned(ws, ("f", l, pack is not None, training, save), rows if rows is not None else M,
+                     lambda a=a, lw=lw, x=x, x_lp=x_lp, l=l: eng._layer_fwd(
+                         lw, x, x_lp, kb, B, S, a.q_lin, a.out_lin, enc.layer_norm1[l], enc.ffns[l].lin1, enc.ffns[l].lin2,
+                         enc.layer_norm2[l], eps, 0.125, eng._site(2 + 4 * l, p_a, training), eng._site(3 + 4 * l, p_h, training),
+                         eng._site(4 + 4 * l, p_h, training), bf, row_valid=row_valid, rows=rows, cu=cu, save=save))
+        x, x_lp = lw["x2"], lw["x2_lp"]
         eng._probe_capture(l, x, B, S, pack)
     eng._probe_inject(Ln, x, x_lp, B, S, pack)
     logits = eng._head_fwd(ws, x_lp, B, S, task_id, eng.pooler.dense, eng.pool_act,
@@ -150,9 +152,11 @@ def backward(eng, dl, sv):
             x_in, x_in_lp = ws["x0"], ws["x0_lp"]
         else:
             x_in, x_in_lp = ws["layers"][l - 1]["x2"], ws["layers"][l - 1]["x2_lp"]
-        eng._layer_bwd(ws, lw, x_in, x_in_lp, ws["kb"], B, S, a.q_lin, a.out_lin, enc.layer_norm1[l], enc.ffns[l].lin1,
-                       enc.ffns[l].lin2, enc.layer_norm2[l], 0.125, eng._site(2 + 4 * l, p_a, training),
-                       eng._site(3 + 4 * l, p_h, training), eng._site(4 + 4 * l, p_h, training), row_valid=ws["row_valid"])
+        eng._planned(ws, ("b", l, False, training, eng.group_wgrad), B * S,
+                     lambda a=a, lw=lw, x_in=x_in, x_in_lp=x_in_lp, l=l: eng._layer_bwd(
+                         ws, lw, x_in, x_in_lp, ws["kb"], B, S, a.q_lin, a.out_lin, enc.layer_norm1[l], enc.ffns[l].lin1,
+                         enc.ffns[l].lin2, enc.layer_norm2[l], 0.125, eng._site(2 + 4 * l, p_a, training),
+                         eng._site(3 + 4 * l, p_h, training), eng._site(4 + 4 * l, p_h, training), row_valid=ws["row_valid"]))
         eng._probe_inject_grad(l, ws["dx"], B, S, None)
         if eng.dp is not None:
             eng.dp.layer_done(eng, l)

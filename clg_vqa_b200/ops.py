@@ -36,6 +36,63 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ----------------------------------------------------------------------------------------------------
+# launch plans: the per-layer launch sequence of the step engine, recorded once and replayed from C
+# ----------------------------------------------------------------------------------------------------
+# A training step issues ~270 kernel launches; built one by one from Python each costs ~20 us of host time (ctypes struct
+# marshalling, tensor-map encoding, launch), i.e. 6-7 ms per step - invisible at 256 samples per GPU (12 ms of GPU work), the
+# bound at the reference's strong-scaling point of 32 per GPU.  The launches of an encoder layer are the same every step
+# except for the packed row count and the dropout seed, so the engine records them once (begin_plan / end_plan: the
+# wrappers below append their filled parameter struct instead of launching) and clg_run_plan replays the list natively,
+# patching those two values.
+OP_GEMM, OP_LN_FWD, OP_LN_BWD, OP_ATTN_FWD, OP_ATTN_BWD, OP_COLSUM = range(6)
+_plan_rec = None
+
+
+def begin_plan():
+    global _plan_rec
+    if _plan_rec is not None:
+        raise ClgError("launch plans do not nest")
+    _plan_rec = []
+
+
+def end_plan():
+    """-> plan object for run_plan (entries table + parameter blob, host memory owned by the returned object)"""
+    global _plan_rec
+    rec, _plan_rec = _plan_rec, None
+    n = len(rec)
+    entries = (L.PlanEntry * max(n, 1))()
+    blob = bytearray()
+    for i, (op, raw, rows_off, seed_off) in enumerate(rec):
+        while len(blob) % 16:
+            blob.append(0)
+        ro = list(rows_off) + [-1] * (2 - len(rows_off))
+        so = list(seed_off) + [-1] * (2 - len(seed_off))
+        entries[i] = L.PlanEntry(op, len(blob), (C.c_int32 * 2)(*ro), (C.c_int32 * 2)(*so))
+        blob += raw
+    buf = (C.c_uint8 * max(len(blob), 16)).from_buffer_copy(bytes(blob) + bytes(max(0, 16 - len(blob))))
+    return {"entries": entries, "n": n, "blob": buf}
+
+
+def run_plan(plan, rows: int, seed: int):
+    L.check(L.load().clg_run_plan(plan["entries"], plan["n"], plan["blob"], int(rows), C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), _stream()),
+            "clg_run_plan")
+    _count(plan["n"])
+
+
+def _issue(op, name, p, rows_fields=(), seed_fields=()):
+    """launch now, or - while a plan is being recorded - keep the filled struct for clg_run_plan"""
+    rec = _plan_rec
+    if rec is not None:
+        cls = type(p)
+        rows_off = [getattr(cls, f).offset for f in rows_fields]
+        seed_off = [getattr(cls, f).offset + L.Dropout.seed.offset for f in seed_fields]
+        rec.append((op, bytes(p), rows_off, seed_off))
+        return
+    L.check(getattr(L.load(), name)(C.byref(p), _stream()), name)
+    _count()
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return CLG_F32
@@ -84,6 +141,7 @@ def gemm(a, b, c, *, a_kmajor=True, b_kmajor=True, M=None, N=None, K=None, alpha
          drop_before_act=False, backend=GEMM_AUTO, split_k=0, colsum=None, group2=None):
     """C[M,N] = epi(alpha * A(m,k) B(n,k)).  a: [M,K] if a_kmajor else [K,M]; b: [N,K] if b_kmajor else [K,N]."""
     _need_cuda(a, b, c)
+    M_given, K_given = M is not None, K is not None          # explicit = the packed row count (patched when a plan is replayed)
     if M is None:
         M = a.shape[0] if a_kmajor else a.shape[1]
     if K is None:
@@ -117,6 +175,9 @@ def gemm(a, b, c, *, a_kmajor=True, b_kmajor=True, M=None, N=None, K=None, alpha
         p.lda2, p.ldb2, p.ldc2 = _ld(a2), _ld(b2), _ld(c2)
         p.mask_bits2 = _ptr(mb2)
         p.M2 = int(a2.shape[0] if a_kmajor else a2.shape[1])
+    if _plan_rec is not None:
+        _issue(OP_GEMM, "clg_gemm", p, [f for f, v in (("M", M_given), ("K", K_given)) if v], ["dropout"] if dropout.p > 0 else [])
+        return c
     rec = _gemm_timing
     if rec is not None:
         # same predicate as clg_gemm's auto dispatch: these launches run gemm_tc_kernel
@@ -161,8 +222,7 @@ def layernorm_fwd(x, gamma, beta, eps, *, y=None, y_lowp=None, mean=None, rstd=N
     p.row_valid = _ptr(row_valid)
     p.valid_pre, p.valid_post = int(valid_pre), int(valid_post)
     p.dropout = dropout.c()
-    L.check(L.load().clg_layernorm_fwd(C.byref(p), _stream()), "clg_layernorm_fwd")
-    _count()
+    _issue(OP_LN_FWD, "clg_layernorm_fwd", p, ["rows"] if rows is not None else [], ["dropout"] if dropout.p > 0 else [])
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx=None, dx_lowp=None, dgamma=None, dbeta=None, dbias=None,
@@ -185,8 +245,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx=None, dx_lowp=None, dgamma=Non
     p.row_valid = _ptr(row_valid)
     p.valid_pre, p.valid_post = int(valid_pre), int(valid_post)
     p.dropout_out, p.dropout_in = dropout_out.c(), dropout_in.c()
-    L.check(L.load().clg_layernorm_bwd(C.byref(p), _stream()), "clg_layernorm_bwd")
-    _count()
+    _issue(OP_LN_BWD, "clg_layernorm_bwd", p, ["rows"] if rows is not None else [],
+           [f for f, d in (("dropout_out", dropout_out), ("dropout_in", dropout_in)) if d.p > 0])
 
 
 def set_gemm_sm_limit(n: int):
@@ -211,8 +271,7 @@ def attention_fwd(qkv, key_bias, ctx, lse, B, S, H, scale, dropout: DropSite = N
     p.scale = float(scale)
     p.dropout = dropout.c()
     p.cu_rows, p.total_rows = _ptr(cu_rows), int(total_rows)
-    L.check(L.load().clg_attention_fwd(C.byref(p), _stream()), "clg_attention_fwd")
-    _count()
+    _issue(OP_ATTN_FWD, "clg_attention_fwd", p, ["total_rows"] if cu_rows is not None else [], ["dropout"] if dropout.p > 0 else [])
 
 
 def attention_bwd(qkv, key_bias, ctx, dctx, lse, dqkv, B, S, H, scale, dropout: DropSite = NO_DROP, cu_rows=None,
@@ -230,8 +289,7 @@ def attention_bwd(qkv, key_bias, ctx, dctx, lse, dqkv, B, S, H, scale, dropout: 
     p.scale = float(scale)
     p.dropout = dropout.c()
     p.cu_rows, p.total_rows = _ptr(cu_rows), int(total_rows)
-    L.check(L.load().clg_attention_bwd(C.byref(p), _stream()), "clg_attention_bwd")
-    _count()
+    _issue(OP_ATTN_BWD, "clg_attention_bwd", p, ["total_rows"] if cu_rows is not None else [], ["dropout"] if dropout.p > 0 else [])
 
 
 def embed_text_fwd(ids, seg, word, pos, type_tab, out, *, pad_id, out_map=None, pos_mode=0, pos_base=0):
@@ -397,6 +455,11 @@ def apply_mask(w, bits, n=None):
 
 def colsum(x, out, M=None, N=None):
     _need_cuda(x, out)
+    if _plan_rec is not None:
+        p = L.ColsumParams(x.data_ptr(), out.data_ptr(), _ld(x), _dt(x), int(x.shape[0] if M is None else M),
+                           int(x.shape[1] if N is None else N), 0)
+        _issue(OP_COLSUM, "clg_colsum", p, ["M"] if M is not None else [], [])
+        return
     L.check(L.load().clg_colsum(x.data_ptr(), _dt(x), _ld(x), int(x.shape[0] if M is None else M),
                                 int(x.shape[1] if N is None else N), out.data_ptr(), _stream()), "clg_colsum")
     _count()

@@ -416,6 +416,26 @@ int clg_pack_mask(const float* mask, uint32_t* bits, int64_t n, clgStream_t stre
 int clg_apply_mask(float* w, const uint32_t* bits, int64_t n, clgStream_t stream);
 /* out[n] += sum_m X[m*ld + n]  (bias gradients that are not fused elsewhere) */
 int clg_colsum(const void* x, int32_t dtype, int64_t ld, int32_t M, int32_t N, float* out, clgStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Launch plans: the launch sequence of an encoder layer (BertEncoder.forward, encoders.py:L848-892, is a Python loop that
+ * dispatches ~1.5 k ops per step; here a layer is ~8 forward / ~13 backward launches) recorded once as filled parameter
+ * structs and replayed natively.  Between two steps only the packed row count and the dropout seed change: entry i patches
+ * `rows` into the int32 fields at rows_off[] and `seed` into the uint64 fields at seed_off[] of its struct (offsets relative
+ * to the struct, -1 = unused), then calls the entry point of `op`.  `blob` is host memory owned by the caller and is modified
+ * in place (one replay at a time per plan).  Stops at the first failing launch and returns its status.
+ * ---------------------------------------------------------------------------------------------- */
+enum { CLG_OP_GEMM = 0, CLG_OP_LN_FWD = 1, CLG_OP_LN_BWD = 2, CLG_OP_ATTN_FWD = 3, CLG_OP_ATTN_BWD = 4, CLG_OP_COLSUM = 5 };
+typedef struct { const void* x; float* out; int64_t ld; int32_t dtype, M, N, _pad; } clgColsumParams;   /* clg_colsum's arguments */
+typedef struct {
+  int32_t op;            /* CLG_OP_* */
+  int32_t off;           /* byte offset of the parameter struct inside blob (16 B aligned) */
+  int32_t rows_off[2];
+  int32_t seed_off[2];
+} clgPlanEntry;
+int clg_run_plan(const clgPlanEntry* entries, int32_t n, void* blob, int32_t rows, uint64_t seed, clgStream_t stream);
+size_t clg_sizeof_plan_entry(void);
+size_t clg_sizeof_colsum_params(void);
 /* key_bias[b, s] = (mask[b, s] != 0) ? 0 : fill  from the int64 masks of the module interface.
  * UC2: two masks concatenated [text | regions], fill -10000 (encoders.py:L978-995).
  * M3P: prefix validity over [regions | text], fill -inf, also writes row_valid (m3p_transformer.py:L59-78). */
