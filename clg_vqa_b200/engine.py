@@ -633,6 +633,8 @@ class Engine:
         if bf and self.pack_enabled and Ln > 0 and S <= (96 if save else 160):   # pipelined attention: bwd S <= 96, fwd S <= 160
             ops.pack_index(tmask, imask, ws["cu"], ws["src"])
             Mp = int(ws["cu"][B])                     # the one host read of the step (launch shapes depend on it)
+            if save and self.dp is not None:
+                self.dp.finalize_plan()              # the row count of the word-row exchange is on the host by now as well
             if Mp < M:
                 ops.rows_gather(x, ws["src"], ws["xp"], n=Mp)
                 ops.rows_gather(x_lp, ws["src"], ws["xp_lp"], n=Mp)

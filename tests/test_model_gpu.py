@@ -310,3 +310,54 @@ def test_fused_step_clears_gradient_arena(precision):
     # a step without a preceding clip (no hot-block map) clears everything as well
     opt.step()
     assert int(torch.count_nonzero(eng.g_flat)) == 0
+
+
+@pytest.mark.parametrize("family", ["uc2", "m3p"])
+def test_launch_plans_replay_the_same_step(family):
+    """Engine._planned (clg_run_plan): the per-layer launch lists recorded on the first step and replayed natively - with
+    the new packed row count and dropout seed patched in - give bit-identical logits, loss and gradients to issuing every
+    launch from Python, over several steps with different batches (different row counts), in training mode."""
+    from clg_vqa_b200 import optim
+    from clg_vqa_b200.encoders import M3PForVLTasks
+    outs = {}
+    for use_plans in (True, False):
+        torch.manual_seed(0)
+        if family == "uc2":
+            cfg = C.uc2_base(2, vocab_size=2048)
+            model = BertForVLTasks(cfg, C.gqa_task_cfg(36), ["TASK15"])
+        else:
+            cfg = C.m3p_base(2, n_words=2048)
+            model = M3PForVLTasks(cfg, C.gqa_task_cfg(100), ["TASK15"])
+        task_cfg = C.gqa_task_cfg(36 if family == "uc2" else 100)
+        model.load_state_dict(S.synth_state_dict(model, seed=9))
+        model.set_precision("bf16")
+        model.to(DEV).train()
+        model.engine.use_plans = use_plans
+        opt = optim.AdamW(optim.grouped_parameters(model, 4e-5, 1e-4), lr=4e-5)
+        rec = []
+        for it in range(4):
+            b = S.synth_batch(8, num_regions=36 if family == "uc2" else 100, num_locs=7 if family == "uc2" else 5, seed=40 + it,
+                              ragged_regions=(family == "uc2"), vocab_size=2048, normalize=(family == "m3p"))
+            loss, _ = TU.ForwardModelsTrain(cfg, task_cfg, DEV, "TASK15", S.batch_tuple(b), model)
+            loss.backward()
+            rec.append((float(loss), model.engine.g_flat.clone(), model.engine.last_rows))
+            optim.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+            model.zero_grad()
+        with torch.no_grad():
+            model.eval()
+            lg = model(b["question"].to(DEV), b["features"].to(DEV), b["spatials"].to(DEV), "TASK15", b["segment_ids"].to(DEV),
+                       b["input_mask"].to(DEV), b["image_mask"].to(DEV))[0].clone()
+        outs[use_plans] = (rec, lg)
+        if use_plans:
+            ws = next(iter(model.engine._ws.values()))
+            assert len(ws.get("plans", {})) >= 2            # the replay path really ran
+    ra, la = outs[True]
+    rb, lb = outs[False]
+    if family == "uc2":
+        assert len({r[2] for r in ra}) > 1                  # the packed row count differed between the steps
+    for (l1, g1, n1), (l2, g2, n2) in zip(ra, rb):
+        assert abs(l1 - l2) <= 1e-5 * abs(l2) and n1 == n2
+        # split-K weight gradients use fp32 atomics: order noise only
+        assert float((g1 - g2).abs().max()) <= 1e-5 * float(g2.abs().max())
+    assert float((la - lb).abs().max()) <= 2e-3 * float(lb.abs().max())      # parameters after 4 steps of atomics-order noise

@@ -86,16 +86,22 @@ def _worker(rank, world, port, out):
         # is never sent, and the gathered + sorted list reduces to the same table
         PAD = 1
         ids3 = torch.randint(0, 6, (NTOK,)); rows3 = torch.randn(NTOK, D)        # many duplicates, some padding ids
+        ex.compact_granule = 1                                   # (256 in production: few distinct all-gather sizes)
         ex.plan_rows(ids3, PAD)
+        ex.finalize_plan()
         plan = ex.plan
+        K = plan["K"]
         local = torch.zeros(V, D).index_add_(0, ids3, rows3)
         send = plan["all_ids"].view(world, NTOK)[rank]
         keep = send != PAD
         ok = ok and bool((send[keep] == ids3[keep]).all()) and send[keep].unique().numel() == int(keep.sum())
         ok = ok and set(send[keep].tolist()) == set(ids3[ids3 != PAD].tolist())
-        carried = torch.where(keep[:, None], local[ids3], torch.zeros_like(rows3))      # what the local pre-reduction leaves
-        gathered = [torch.zeros_like(carried) for _ in range(world)]
-        dist.all_gather(gathered, carried)
+        ok = ok and K < NTOK and K >= int(keep.sum())            # duplicates and padding do not travel
+        carried = torch.where(keep[:, None], local[ids3], torch.full_like(rows3, float("nan")))     # what the local pre-reduction leaves
+        carried_c = carried[plan["mine"].long()]                 # compaction: the carriers first, in position order
+        ok = ok and bool(torch.isfinite(carried_c[:int(keep.sum())]).all())
+        gathered = [torch.zeros_like(carried_c) for _ in range(world)]
+        dist.all_gather(gathered, carried_c)
         all_rows = torch.cat(gathered)
         t3 = torch.zeros(V, D)
         so, od = plan["all_sorted"], plan["all_order"]
@@ -106,7 +112,8 @@ def _worker(rank, world, port, out):
         ref3 = torch.zeros(V, D)
         for i, r in zip(all_i3, all_r3):
             ref3.index_add_(0, i[i != PAD], r[i != PAD])
-        ok = ok and torch.allclose(t3, ref3, atol=1e-5) and bool(torch.equal(so, torch.sort(plan["all_ids"], stable=True).values))
+        ok = ok and torch.allclose(t3, ref3, atol=1e-5) and bool(torch.equal(so, torch.sort(plan["ids_c"], stable=True).values))
+        ok = ok and plan["ids_c"].numel() == world * K
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
