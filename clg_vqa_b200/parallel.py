@@ -164,10 +164,9 @@ class GradExchange:
         self.row_ids, self.row_vals = [], []
         ops.segment_sum_rows(rows, plan["order"], plan["sorted"], None, plan["pad"], ids_out=plan["scratch"])
         K = plan["K"]
-        send = rows
-        if K < plan["n"]:
-            send = torch.empty((K, rows.shape[1]), dtype=rows.dtype, device=rows.device)
-            ops.rows_gather(rows, plan["mine"], send, n=K)
+        # the gathered id list is in compacted order (carriers first) even when every row travels: the rows must follow it
+        send = torch.empty((K, rows.shape[1]), dtype=rows.dtype, device=rows.device)
+        ops.rows_gather(rows, plan["mine"], send, n=K)
         self._mark("rows_prereduced")
         all_rows = torch.empty((self.world * K, rows.shape[1]), dtype=rows.dtype, device=rows.device)
         h = dist.all_gather_into_tensor(all_rows.view(-1), send.reshape(-1), group=self.group, async_op=True)
