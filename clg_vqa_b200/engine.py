@@ -459,7 +459,9 @@ class Engine:
             Cc = self._wb(clf.logit_fc[0])[0].shape[0]
             A = clf.logit_fc[3].bias.shape[0]
             heads[task] = {"C": Cc, "A": A, "uc": E(B, Cc), "hc": E(B, Cc), "mc": E(B), "rc": E(B),
-                           "hln": E(B, Cc, dtype=lp), "logits": E(B, A)}
+                           # logits rows padded to a 16 B pitch (1842 -> 1844 fp32): the GEMM epilogue then stores them with
+                           # vector instructions instead of one column per lane; callers see the [B, A] view
+                           "hln": E(B, Cc, dtype=lp), "logits": E(B, (A + 3) // 4 * 4)[:, :A]}
         ws["heads"] = heads
         if training:
             ws["dx"] = E(M, d); ws["dy"] = E(M, d)
