@@ -239,6 +239,15 @@ class _VLTasksBase(nn.Module):
     def engine(self):
         return self._get_engine()
 
+    def zero_grad(self, set_to_none: bool = True):
+        """nn.Module.zero_grad; after the fused optimiser step the gradient arena is already all zero (the AdamW kernel
+        cleared what it read) and the next backward re-attaches it - walking 215 parameters to drop their `.grad` views
+        would only cost host time (1 ms per step at small batches)."""
+        eng = self.__dict__.get("_engine")
+        if eng is not None and eng.grads_consumed and eng.grads_zeroed:
+            return
+        super().zero_grad(set_to_none=set_to_none)
+
     def set_precision(self, mode: str):
         """'bf16' (tcgen05 GEMMs, bf16 operands, fp32 accumulate / residual stream) or 'fp32'
         (correctness mode: fp32 FFMA GEMMs)."""

@@ -113,9 +113,21 @@ class Engine:
         return mod._parameters[which], None
 
     def _structure_signature(self):
+        """(name, storage pointer) of every parameter: changes when parameters are re-created / moved / renamed (model.to(),
+        prune re-parametrisation).  Evaluated on every forward, so it walks a cached module list and the modules'
+        own `_parameters` dicts instead of the recursive named_parameters() generators (3 x cheaper)."""
+        mods = self.__dict__.get("_sig_modules")
+        if mods is None:
+            mods = [(n, m) for n, m in self.model.named_modules()]
+            self.__dict__["_sig_modules"] = mods
         sig = []
-        for name, p in self.model.named_parameters():
-            sig.append((name, p.data_ptr() if p.is_cuda else -1))
+        seen = set()
+        for n, m in mods:
+            for k, p in m._parameters.items():
+                if p is None or id(p) in seen:
+                    continue
+                seen.add(id(p))
+                sig.append((n, k, p.data_ptr() if p.is_cuda else -1))
         return tuple(sig)
 
     def _collect_uc2(self):
@@ -326,7 +338,7 @@ class Engine:
         if sig != self._struct_sig:
             # parameters were re-created / moved (model.to(), prune re-parametrisation renames keep the
             # same tensors but change names) -> rebuild the arenas from the current values
-            same_ptrs = [x[1] for x in sig] == [x[1] for x in self._struct_sig]
+            same_ptrs = [x[-1] for x in sig] == [x[-1] for x in self._struct_sig]
             if same_ptrs:
                 self._struct_sig = sig
                 self._shadow_versions = None
@@ -749,13 +761,14 @@ class Engine:
             lo, hi = self._table_blocks
             self._touched[lo:hi].zero_()
             self._touch_valid = True        # from here on every write into the table gradient is marked (mark_word_rows)
-            for s in self.slots:
-                o = s.start
-                for p in s.params:
-                    n = p.numel()
-                    if p.requires_grad and s.has_grad:
-                        p.grad = self.g_flat[o:o + n].view(p.shape)
-                    o += n
+            if dropped:                     # (views that are still attached stay: the step only cleared their contents)
+                for s in self.slots:
+                    o = s.start
+                    for p in s.params:
+                        n = p.numel()
+                        if p.requires_grad and s.has_grad:
+                            p.grad = self.g_flat[o:o + n].view(p.shape)
+                        o += n
             self.grads_consumed = False
         self.grads_zeroed = False       # this backward writes the arena
 

@@ -33,7 +33,8 @@ def _count(n=1):
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    # raw handle of torch's current stream (torch.cuda.current_stream() builds a Stream object: 15 us per launch)
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 # ----------------------------------------------------------------------------------------------------

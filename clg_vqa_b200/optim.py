@@ -13,6 +13,7 @@ norm reduction (`clg_adamw_step`, `clg_sumsq`); no per-parameter launches, no ho
 """
 from __future__ import annotations
 
+import inspect
 import math
 import weakref
 
@@ -31,6 +32,28 @@ def register_engine(engine):
     for s in engine.slots:
         for p in s.params:
             _ENGINE_OF_PARAM[id(p)] = engine
+
+
+def _engine_of_parameters_generator(parameters):
+    """`clip_grad_norm_(model.parameters(), ...)` is called every step; materialising that generator walks the whole module
+    tree (0.4 ms of host time).  When the argument IS the un-started `Module.parameters()` generator of a model whose
+    parameters all live in one engine, the engine is returned without consuming it."""
+    try:
+        if not inspect.isgenerator(parameters) or parameters.gi_code.co_name != "parameters" or parameters.gi_frame is None:
+            return None
+        if inspect.getgeneratorstate(parameters) != "GEN_CREATED":
+            return None
+        loc = parameters.gi_frame.f_locals
+        owner = loc.get("self")
+        if not isinstance(owner, torch.nn.Module) or not loc.get("recurse", True):
+            return None
+        owner = getattr(owner, "module", owner)
+        eng = getattr(owner, "__dict__", {}).get("_engine")
+        if eng is None or eng.p_flat is None or eng.model is not owner:
+            return None
+        return eng
+    except Exception:
+        return None
 
 
 def _engine_for(params):
@@ -55,8 +78,12 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0):
     """torch.nn.utils.clip_grad_norm_ for engine-owned parameters: computes the global L2 norm of the
     gradient arena on the device (no host sync) and defers the scaling into the fused AdamW kernel.
     Falls back to torch's implementation for parameters that are not engine-owned."""
-    params = [p for p in (parameters if not isinstance(parameters, torch.Tensor) else [parameters])]
-    eng = _engine_for(params)
+    eng = _engine_of_parameters_generator(parameters) if float(norm_type) == 2.0 else None
+    if eng is not None:
+        params = None                      # `model.parameters()` of an engine-owned model: no need to walk the module tree
+    else:
+        params = [p for p in (parameters if not isinstance(parameters, torch.Tensor) else [parameters])]
+        eng = _engine_for(params)
     if eng is None or float(norm_type) != 2.0:
         scale = float(getattr(eng, "grad_scale", 1.0)) if eng is not None else 1.0
         if scale != 1.0:        # data parallel: the arena holds the SUM over ranks; clip the average, like the reference
