@@ -91,9 +91,101 @@ sumsq_final_kernel(const float* __restrict__ partials, int n, float* __restrict_
   if (threadIdx.x == 0) out[0] += (float)sh[0];
 }
 
+// One 2048-element chunk of tensor `tm` (8 consecutive elements per thread).  `cold`: the warp's 256-element block has
+// g = m = v = 0 (never held a non-zero gradient).
+template <bool UPDATE>
+__device__ __forceinline__ void adamw_chunk(const clgAdamWParams& p, const int64_t c, const clgTensorMeta& tm, const bool cold,
+                                            const float coef) {
+  const int64_t base = c * CHUNK + (int64_t)threadIdx.x * 8;
+  const int64_t rel = base - tm.start;          // element offset inside the tensor
+  if (rel >= tm.numel) return;                  // tail padding of the tensor's last chunk (never written)
+  // g = m = v = 0: the update reduces to the decoupled decay p <- fma(-lr*wd, p, p).  Below 2^-25 the product is under
+  // half an ulp of p, so the rounded result IS p (bit-identical to the dense update): with the reference's settings
+  // (lr <= 1e-4, weight decay 1e-4, train_task.py:L249-267) the untouched word-embedding rows cost no traffic at all
+  if (cold && !(tm.lr * tm.wd >= 2.98023224e-8f)) return;
+  float pv[8];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(p.p + base);
+    const float4 b = *reinterpret_cast<const float4*>(p.p + base + 4);
+    pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w; pv[4] = b.x; pv[5] = b.y; pv[6] = b.z; pv[7] = b.w;
+  }
+  if (cold) {
+    // the dense formulas with g = m = v = 0 reduce to the decoupled decay alone (bit-identical: p - step*(0/eps) == p)
+    const float decay = tm.lr * tm.wd;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pv[j] = pv[j] - decay * pv[j];
+    *reinterpret_cast<float4*>(p.p + base) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    *reinterpret_cast<float4*>(p.p + base + 4) = make_float4(pv[4], pv[5], pv[6], pv[7]);
+  } else if (UPDATE) {
+    float gv[8], mv[8], vv[8];
+    {
+      const float4 a = *reinterpret_cast<const float4*>(p.g + base);        // plain loads: g may be cleared below
+      const float4 b = *reinterpret_cast<const float4*>(p.g + base + 4);
+      gv[0] = a.x; gv[1] = a.y; gv[2] = a.z; gv[3] = a.w; gv[4] = b.x; gv[5] = b.y; gv[6] = b.z; gv[7] = b.w;
+      const float4 c0 = *reinterpret_cast<const float4*>(p.m + base);
+      const float4 c1 = *reinterpret_cast<const float4*>(p.m + base + 4);
+      mv[0] = c0.x; mv[1] = c0.y; mv[2] = c0.z; mv[3] = c0.w; mv[4] = c1.x; mv[5] = c1.y; mv[6] = c1.z; mv[7] = c1.w;
+      const float4 d0 = *reinterpret_cast<const float4*>(p.v + base);
+      const float4 d1 = *reinterpret_cast<const float4*>(p.v + base + 4);
+      vv[0] = d0.x; vv[1] = d0.y; vv[2] = d0.z; vv[3] = d0.w; vv[4] = d1.x; vv[5] = d1.y; vv[6] = d1.z; vv[7] = d1.w;
+    }
+    const float step_size = tm.lr * sqrtf(p.bias_c2) / p.bias_c1;
+    const float decay = tm.lr * tm.wd;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float g = gv[j] * coef;
+      mv[j] = mv[j] * p.beta1 + (1.f - p.beta1) * g;
+      vv[j] = vv[j] * p.beta2 + (1.f - p.beta2) * g * g;
+      const float denom = sqrtf(vv[j]) + p.eps;
+      float w = pv[j] - step_size * (mv[j] / denom);
+      if (tm.wd > 0.f) w = w - decay * w;
+      pv[j] = w;
+    }
+    *reinterpret_cast<float4*>(p.p + base) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    *reinterpret_cast<float4*>(p.p + base + 4) = make_float4(pv[4], pv[5], pv[6], pv[7]);
+    *reinterpret_cast<float4*>(p.m + base) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+    *reinterpret_cast<float4*>(p.m + base + 4) = make_float4(mv[4], mv[5], mv[6], mv[7]);
+    *reinterpret_cast<float4*>(p.v + base) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    *reinterpret_cast<float4*>(p.v + base + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
+    if (p.zero_grad) {                                                        // after every load of this thread's g
+      float* gz = const_cast<float*>(p.g) + base;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(gz) = z4;
+      *reinterpret_cast<float4*>(gz + 4) = z4;
+    }
+  }
+  if (p.shadow && tm.shadow_off >= 0) {
+    if (tm.mask_off >= 0) {
+      // 8 consecutive mask bits; rel is a multiple of 8 and mask_off a multiple of 32
+      const int64_t bit0 = tm.mask_off + rel;
+      const uint32_t bits = (p.mask_bits[bit0 >> 5] >> (bit0 & 31)) & 0xffu;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pv[j] *= ((bits >> j) & 1u) ? 1.f : 0.f;
+    }
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(pv[0], pv[1]);
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(pv[2], pv[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[4], pv[5]);
+    __nv_bfloat162 h3 = __floats2bfloat162_rn(pv[6], pv[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>((bf16*)p.shadow + tm.shadow_off + rel) = u;
+  }
+}
+
+// A CTA walks the chunks c = blockIdx.x, + gridDim.x, ...  The per-chunk header (tensor index -> clgTensorMeta, the 8
+// hot bytes of the chunk's 256-element blocks) is a chain of three dependent loads; two thirds of the chunks of the UC2
+// arena are cold word-table blocks for which that chain is all there is.  The headers of HDR chunks are therefore fetched
+// at once - lane j of warp 0 takes the j-th chunk of the batch - into shared memory, and the loop over the batch then
+// reads no global memory but the arenas themselves.
+static constexpr int HDR = 32;
+
 template <bool UPDATE>
 __global__ void __launch_bounds__(OPT_THREADS)
 adamw_kernel(const clgAdamWParams p) {
+  __shared__ clgTensorMeta s_tm[HDR];
+  __shared__ unsigned long long s_hot[HDR];
+  __shared__ int s_t[HDR];
   const int64_t nchunks = p.n / CHUNK;
   float coef = p.gscale;
   if (UPDATE && p.sumsq) {
@@ -101,87 +193,40 @@ adamw_kernel(const clgAdamWParams p) {
     const float c = p.max_norm / (total + 1e-6f);
     if (c < 1.f) coef *= c;
   }
-  for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-    const int t = p.chunk_tensor[c];
-    const int64_t base = c * CHUNK + (int64_t)threadIdx.x * 8;
-    const bool zero_g = UPDATE && p.zero_grad;
-    float* gz = const_cast<float*>(p.g) + base;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t < 0) {                                  // no optimiser entry: its gradient (if any was written) is only cleared
-      if (zero_g) { *reinterpret_cast<float4*>(gz) = z4; *reinterpret_cast<float4*>(gz + 4) = z4; }
-      continue;
-    }
-    const clgTensorMeta tm = p.tensors[t];
-    const int64_t rel = base - tm.start;          // element offset inside the tensor
-    if (rel >= tm.numel) continue;                // tail padding of the tensor's last chunk (never written)
-    const bool cold = UPDATE && p.hot && !p.hot[base >> 8];      // warp-uniform: a warp covers one 256-element block
-    // g = m = v = 0: the update reduces to the decoupled decay p <- fma(-lr*wd, p, p).  Below 2^-25 the product is under
-    // half an ulp of p, so the rounded result IS p (bit-identical to the dense update): with the reference's settings
-    // (lr <= 1e-4, weight decay 1e-4, train_task.py:L249-267) the untouched word-embedding rows cost no traffic at all
-    if (cold && !(tm.lr * tm.wd >= 2.98023224e-8f)) continue;
-    float pv[8];
-    {
-      const float4 a = *reinterpret_cast<const float4*>(p.p + base);
-      const float4 b = *reinterpret_cast<const float4*>(p.p + base + 4);
-      pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w; pv[4] = b.x; pv[5] = b.y; pv[6] = b.z; pv[7] = b.w;
-    }
-    if (cold) {
-      // the dense formulas with g = m = v = 0 reduce to the decoupled decay alone (bit-identical: p - step*(0/eps) == p)
-      const float decay = tm.lr * tm.wd;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) pv[j] = pv[j] - decay * pv[j];
-      *reinterpret_cast<float4*>(p.p + base) = make_float4(pv[0], pv[1], pv[2], pv[3]);
-      *reinterpret_cast<float4*>(p.p + base + 4) = make_float4(pv[4], pv[5], pv[6], pv[7]);
-    } else if (UPDATE) {
-      float gv[8], mv[8], vv[8];
-      {
-        const float4 a = *reinterpret_cast<const float4*>(p.g + base);        // plain loads: g may be cleared below
-        const float4 b = *reinterpret_cast<const float4*>(p.g + base + 4);
-        gv[0] = a.x; gv[1] = a.y; gv[2] = a.z; gv[3] = a.w; gv[4] = b.x; gv[5] = b.y; gv[6] = b.z; gv[7] = b.w;
-        const float4 c0 = *reinterpret_cast<const float4*>(p.m + base);
-        const float4 c1 = *reinterpret_cast<const float4*>(p.m + base + 4);
-        mv[0] = c0.x; mv[1] = c0.y; mv[2] = c0.z; mv[3] = c0.w; mv[4] = c1.x; mv[5] = c1.y; mv[6] = c1.z; mv[7] = c1.w;
-        const float4 d0 = *reinterpret_cast<const float4*>(p.v + base);
-        const float4 d1 = *reinterpret_cast<const float4*>(p.v + base + 4);
-        vv[0] = d0.x; vv[1] = d0.y; vv[2] = d0.z; vv[3] = d0.w; vv[4] = d1.x; vv[5] = d1.y; vv[6] = d1.z; vv[7] = d1.w;
+  const int warp = threadIdx.x >> 5;
+  for (int64_t c0 = blockIdx.x; c0 < nchunks; c0 += (int64_t)HDR * gridDim.x) {
+    if (threadIdx.x < HDR) {
+      const int64_t c = c0 + (int64_t)threadIdx.x * gridDim.x;
+      int t = -2;                                   // -2: past the end of the arena
+      unsigned long long h = ~0ull;
+      if (c < nchunks) {
+        t = __ldg(p.chunk_tensor + c);
+        if (UPDATE && p.hot) h = __ldg(reinterpret_cast<const unsigned long long*>(p.hot) + c);   // CHUNK / 256 = 8 bytes
+        if (t >= 0) s_tm[threadIdx.x] = p.tensors[t];
       }
-      const float step_size = tm.lr * sqrtf(p.bias_c2) / p.bias_c1;
-      const float decay = tm.lr * tm.wd;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float g = gv[j] * coef;
-        mv[j] = mv[j] * p.beta1 + (1.f - p.beta1) * g;
-        vv[j] = vv[j] * p.beta2 + (1.f - p.beta2) * g * g;
-        const float denom = sqrtf(vv[j]) + p.eps;
-        float w = pv[j] - step_size * (mv[j] / denom);
-        if (tm.wd > 0.f) w = w - decay * w;
-        pv[j] = w;
-      }
-      *reinterpret_cast<float4*>(p.p + base) = make_float4(pv[0], pv[1], pv[2], pv[3]);
-      *reinterpret_cast<float4*>(p.p + base + 4) = make_float4(pv[4], pv[5], pv[6], pv[7]);
-      *reinterpret_cast<float4*>(p.m + base) = make_float4(mv[0], mv[1], mv[2], mv[3]);
-      *reinterpret_cast<float4*>(p.m + base + 4) = make_float4(mv[4], mv[5], mv[6], mv[7]);
-      *reinterpret_cast<float4*>(p.v + base) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-      *reinterpret_cast<float4*>(p.v + base + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
-      if (zero_g) { *reinterpret_cast<float4*>(gz) = z4; *reinterpret_cast<float4*>(gz + 4) = z4; }   // after every load
+      s_t[threadIdx.x] = t;
+      s_hot[threadIdx.x] = h;
     }
-    if (p.shadow && tm.shadow_off >= 0) {
-      if (tm.mask_off >= 0) {
-        // 8 consecutive mask bits; rel is a multiple of 8 and mask_off a multiple of 32
-        const int64_t bit0 = tm.mask_off + rel;
-        const uint32_t bits = (p.mask_bits[bit0 >> 5] >> (bit0 & 31)) & 0xffu;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) pv[j] *= ((bits >> j) & 1u) ? 1.f : 0.f;
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < HDR; ++j) {
+      const int t = s_t[j];
+      if (t == -2) break;
+      const int64_t c = c0 + (int64_t)j * gridDim.x;
+      if (t < 0) {                                  // no optimiser entry: its gradient (if any was written) is only cleared
+        if (UPDATE && p.zero_grad) {
+          float* gz = const_cast<float*>(p.g) + c * CHUNK + (int64_t)threadIdx.x * 8;
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(gz) = z4;
+          *reinterpret_cast<float4*>(gz + 4) = z4;
+        }
+        continue;
       }
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(pv[0], pv[1]);
-      __nv_bfloat162 h1 = __floats2bfloat162_rn(pv[2], pv[3]);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[4], pv[5]);
-      __nv_bfloat162 h3 = __floats2bfloat162_rn(pv[6], pv[7]);
-      uint4 u;
-      u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-      u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-      *reinterpret_cast<uint4*>((bf16*)p.shadow + tm.shadow_off + rel) = u;
+      // warp-uniform: a warp covers one 256-element block (byte `warp` of the chunk's hot word)
+      const bool cold = UPDATE && ((s_hot[j] >> (8 * warp)) & 0xffull) == 0ull;
+      adamw_chunk<UPDATE>(p, c, s_tm[j], cold, coef);
     }
+    __syncthreads();                                // the batch is consumed: its header slots may be rewritten
   }
 }
 
@@ -224,6 +269,7 @@ extern "C" int clg_mark_rows(const int64_t* ids, int64_t n, int64_t row_elems, i
 extern "C" int clg_adamw_step(const clgAdamWParams* p, clgStream_t stream) {
   using namespace clg;
   if (!p || !p->p || !p->g || !p->m || !p->v || !p->chunk_tensor || !p->tensors || p->n <= 0 || (p->n % CHUNK)) return CLG_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(p->hot) & 7) return CLG_ERR_ARG;      // the kernel reads a chunk's 8 hot bytes as one word
   int st = require_sm100();
   if (st != CLG_OK) return st;
   const int64_t nchunks = p->n / CHUNK;

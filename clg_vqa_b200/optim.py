@@ -69,6 +69,32 @@ def _engine_for(params):
     return eng
 
 
+def _owner_engine(opt):
+    """the engine that owns ALL of `opt`'s parameters, or None (cached per optimiser; re-derived when its groups change)"""
+    key = (len(opt.param_groups), id(opt.param_groups[0]["params"][0]) if opt.param_groups and opt.param_groups[0]["params"] else 0)
+    hint = opt.__dict__.get("_eng_hint")
+    if hint is not None and hint[0] == key:
+        eng = hint[1]() if hint[1] is not None else None
+        if eng is not None and eng.p_flat is not None:
+            return eng
+    eng = _engine_for([p for g in opt.param_groups for p in g["params"]])
+    opt.__dict__["_eng_hint"] = (key, weakref.ref(eng) if eng is not None else None)
+    return eng
+
+
+def _clip_consumer(eng) -> bool:
+    """True when a live AdamW of this module steps the engine's parameters: its step (fused or per-parameter) applies the
+    clip coefficient that clip_grad_norm_ deferred"""
+    return any(_owner_engine(o) is eng for o in list(_OPTIMIZERS))
+
+
+def _mark_prescaled(eng):
+    """the arena was just multiplied by eng.grad_scale (1/world): the engine's AdamW instances must not apply it again"""
+    for o in list(_OPTIMIZERS):
+        if getattr(o, "grad_scale", 1.0) != 1.0 and _owner_engine(o) is eng:
+            o._grads_prescaled = True
+
+
 _OPTIMIZERS = weakref.WeakSet()      # live AdamW instances (clip_grad_norm_'s torch fallback tells them it pre-scaled)
 _FUSED_ZERO = os.environ.get("CLG_FUSED_ZERO", "1") != "0"    # the fused step clears the gradients it consumes
 _PENDING_CLIP = {}   # id(engine) -> max_norm recorded by clip_grad_norm_ for the next fused step
@@ -88,9 +114,7 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0):
         scale = float(getattr(eng, "grad_scale", 1.0)) if eng is not None else 1.0
         if scale != 1.0:        # data parallel: the arena holds the SUM over ranks; clip the average, like the reference
             eng.g_flat.mul_(scale)
-            for o in list(_OPTIMIZERS):
-                if getattr(o, "grad_scale", 1.0) != 1.0 and _engine_for([p for g in o.param_groups for p in g["params"]]) is eng:
-                    o._grads_prescaled = True
+            _mark_prescaled(eng)
         return torch.nn.utils.clip_grad_norm_(params, max_norm, norm_type)
     eng._sumsq.zero_()
     # the norm pass also marks which 256-element blocks of the gradient arena hold a non-zero (eng._hot); the fused
@@ -98,9 +122,19 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0):
     sparse = (eng._table_blocks[0], eng._table_blocks[1], eng._touched) if eng._touch_valid else None
     ops.sumsq(eng.g_flat, eng._partials, eng._sumsq, hot=eng._hot, sparse=sparse)
     eng._hot_valid = True
-    _PENDING_CLIP[id(eng)] = float(max_norm)
+    scale = float(getattr(eng, "grad_scale", 1.0))
     # the norm of the AVERAGED gradient (what the reference logs and clips after apex's 1/world)
-    return eng._sumsq.sqrt() * float(getattr(eng, "grad_scale", 1.0))
+    norm = eng._sumsq.sqrt() * scale
+    if _clip_consumer(eng):
+        _PENDING_CLIP[id(eng)] = float(max_norm)       # applied inside the next AdamW.step of this engine's parameters
+    else:
+        # no AdamW of this module owns the engine's parameters (a foreign optimiser steps them): nobody would pick the
+        # deferred coefficient up, so the gradients are scaled here, like torch.nn.utils.clip_grad_norm_ (still no host sync)
+        coef = (float(max_norm) / (norm + 1e-6)).clamp(max=1.0)
+        eng.g_flat.mul_(coef * scale if scale != 1.0 else coef)
+        if scale != 1.0:
+            _mark_prescaled(eng)
+    return norm
 
 
 class AdamW(Optimizer):

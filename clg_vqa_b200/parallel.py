@@ -282,10 +282,12 @@ def attach(model, optimizer=None, world_size: Optional[int] = None, group=None) 
         import os
         from . import ops
         ops.set_gemm_sm_limit(int(os.environ.get("CLG_DP_GEMM_SMS", "0")))
+    eng.grad_scale = 1.0 / ex.world                      # clip_grad_norm_ reports / clips the AVERAGED gradient's norm
     if optimizer is not None:
         if hasattr(optimizer, "grad_scale"):
             optimizer.grad_scale = 1.0 / ex.world        # our AdamW: fused kernel and per-parameter path both honour it
         else:
-            ex.scale_after_exchange = 1.0 / ex.world     # foreign optimiser: average the arena right after the exchange
-    eng.grad_scale = 1.0 / ex.world                      # clip_grad_norm_ reports / clips the AVERAGED gradient's norm
+            # foreign optimiser: the arena is averaged right after the exchange, so what clip_grad_norm_ sees IS the average
+            ex.scale_after_exchange = 1.0 / ex.world
+            eng.grad_scale = 1.0
     return ex

@@ -200,3 +200,60 @@ def test_dp_bucket_ranges_cover_every_layer_once(monkeypatch):
         assert cover[0][0] == 0 and cover[-1][1] == o
         gaps = [(cover[i][1], cover[i + 1][0]) for i in range(len(cover) - 1) if cover[i][1] != cover[i + 1][0]]
         assert gaps == [(wslot.start, wslot.start + _pad(wslot.numel))]                           # only the word table is skipped
+
+
+class _FakeEngine:
+    """just enough of engine.Engine for optim's host logic (no device, no kernels)"""
+
+    def __init__(self, params):
+        n = sum(p.numel() for p in params)
+        self.p_flat = torch.zeros(n)
+        self.g_flat = torch.zeros(n)
+        self._slot_of_param = {id(p): object() for p in params}
+        self._partials = torch.zeros(8)
+        self._sumsq = torch.zeros(1)
+        self._hot = torch.zeros(1, dtype=torch.uint8)
+        self._hot_valid = False
+        self._touch_valid = False
+        self._table_blocks = (0, 0)
+        self._touched = None
+        self.grad_scale = 1.0
+
+
+def test_deferred_clip_is_applied_at_once_without_an_adamw_of_ours(monkeypatch):
+    """optim.clip_grad_norm_ defers the clip coefficient into the next fused AdamW step.  When the engine's parameters are
+    stepped by a foreign optimiser nobody would consume it: the gradients must then be scaled immediately, like
+    torch.nn.utils.clip_grad_norm_ (reference call site train_task.py:L326-338)."""
+    monkeypatch.setattr(optim.ops, "sumsq", lambda g, partials, out, hot=None, sparse=None: out.add_((g.double() ** 2).sum().float()))
+    params = [torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(5))]
+    eng = _FakeEngine(params)
+    for p in params:
+        optim._ENGINE_OF_PARAM[id(p)] = eng
+    try:
+        eng.g_flat.copy_(torch.arange(8, dtype=torch.float32))
+        norm0 = float(eng.g_flat.norm())
+        foreign = torch.optim.SGD(params, lr=0.1)                    # noqa: F841  (not one of ours: no consumer)
+        out = optim.clip_grad_norm_(params, 1.0)
+        assert abs(float(out) - norm0) < 1e-5
+        assert abs(float(eng.g_flat.norm()) - 1.0) < 1e-4 and id(eng) not in optim._PENDING_CLIP
+        # below the threshold nothing moves
+        before = eng.g_flat.clone()
+        optim.clip_grad_norm_(params, 10.0)
+        assert torch.equal(before, eng.g_flat)
+        # with an AdamW of this module over the same parameters the coefficient is deferred and the arena left alone
+        ours = optim.AdamW([{"params": [p]} for p in params], lr=1e-3)
+        eng.g_flat.copy_(torch.arange(8, dtype=torch.float32))
+        optim.clip_grad_norm_(params, 1.0)
+        assert abs(float(eng.g_flat.norm()) - norm0) < 1e-5 and optim._PENDING_CLIP.pop(id(eng)) == 1.0
+        assert optim._owner_engine(ours) is eng
+        # data parallel with a foreign optimiser: the arena already holds the average, the norm is not scaled again
+        del ours
+        import gc
+        gc.collect()
+        eng.grad_scale = 1.0
+        eng.g_flat.fill_(2.0)
+        assert abs(float(optim.clip_grad_norm_(params, 100.0)) - 2.0 * math.sqrt(8)) < 1e-5
+    finally:
+        for p in params:
+            optim._ENGINE_OF_PARAM.pop(id(p), None)
+        optim._PENDING_CLIP.pop(id(eng), None)
