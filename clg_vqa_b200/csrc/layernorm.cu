@@ -148,6 +148,21 @@ ln_bwd_vec_kernel(const clgLayerNormBwdParams p, const Drop drop_out, const Drop
       d[i] = *reinterpret_cast<const float4*>(dyr + 4 * (lane + 32 * i));
       xh[i] = *reinterpret_cast<const float4*>(xr + 4 * (lane + 32 * i));
     }
+    {
+      // the warp's next row: one 128 B line per lane towards L2 while this row is being reduced (the saved forward
+      // activation x comes from DRAM; both register sets stay live to the end of the row, so there is no room to
+      // load the next row early).  Step-level A/B on one box: 12.03 / 12.06 ms with, 12.11 / 12.17 ms without; the
+      // kernel timed alone (both inputs in L2, or both in DRAM) does not change (profiles/r02_ln_micro_smem_gamma.txt)
+      const int64_t rn = r + (int64_t)gridDim.x * LN_WARPS;
+      if (rn < p.rows) {
+        const float* xn = p.x + rn * p.ldx;
+        const float* dn = p.dy + map_row(p.dy_map, rn) * p.lddy;
+        for (int l = lane; l < C4 * 4; l += 32) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(xn + 32 * l));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(dn + 32 * l));
+        }
+      }
+    }
     const float mean = p.mean[r], rstd = p.rstd[r];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
