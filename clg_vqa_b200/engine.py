@@ -87,7 +87,8 @@ class Engine:
         # dropout stream: keyed on torch's seed (torch.manual_seed / args.seed picks the stream, train_task.py:L189-191),
         # the rank (parallel.attach folds it in: independent masks per process, as with per-process RNGs) and the step
         # counter (saved / restored by checkpoint.save / resume)
-        self.base_seed = (int(torch.initial_seed()) ^ 0x5EED) & 0x7FFFFFFFFFFFFFFF
+        self.seed_root = (int(torch.initial_seed()) ^ 0x5EED) & 0x7FFFFFFFFFFFFFFF    # rank-free part: what a checkpoint stores
+        self.rank_salt = 0                                                              # set by parallel.attach
         self.step_counter = 0
         self.grads_consumed = True       # True: next backward zeroes the gradient arena first
         self.pack_enabled = os.environ.get("CLG_PACK", "1") != "0"   # drop masked positions before the encoder layers
@@ -504,11 +505,21 @@ class Engine:
     def step_seed(self) -> int:
         return (self.base_seed * 0x9E3779B1 + self.step_counter) & 0x7FFFFFFFFFFFFFFF
 
+    @property
+    def base_seed(self) -> int:
+        return (self.seed_root ^ self.rank_salt) & 0x7FFFFFFFFFFFFFFF
+
+    def set_rank(self, rank: int):
+        """independent dropout masks per data-parallel rank (the reference's processes have independent RNG streams)"""
+        self.rank_salt = ((int(rank) + 1) * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
+
     def rng_state(self) -> dict:
-        return {"base_seed": int(self.base_seed), "step_counter": int(self.step_counter)}
+        """the rank-free seed and the step counter: rank 0 writes the checkpoint, every rank restores it (before or after
+        parallel.attach) and still draws its own masks"""
+        return {"base_seed": int(self.seed_root), "step_counter": int(self.step_counter)}
 
     def set_rng_state(self, st: dict):
-        self.base_seed = int(st["base_seed"])
+        self.seed_root = int(st["base_seed"]) & 0x7FFFFFFFFFFFFFFF
         self.step_counter = int(st["step_counter"])
 
     def _site(self, idx: int, p: float, training: bool) -> DropSite:
@@ -570,7 +581,7 @@ class Engine:
         if self.device is None or self.device != dev or self.p_flat is None:
             self.adopt(dev)
         want_grad = torch.is_grad_enabled()
-        with torch.no_grad():
+        with torch.no_grad(), ops.nvtx_range("clg.forward"):
             self._refresh()
             training = bool(self.model.training)
             feats = input_imgs.contiguous()
@@ -683,6 +694,12 @@ class Engine:
         """run the launches `fn` issues - recorded on first use, replayed natively afterwards (only the packed row count and
         the dropout seed differ between steps).  Falls back to issuing them one by one when a test hook or the per-GEMM
         timer needs to see the individual launches."""
+        if ops.NVTX:
+            with ops.nvtx_range("clg.layer%d.%s" % (key[1], "fwd" if key[0] == "f" else "bwd")):
+                return self._planned_run(ws, key, rows, fn)
+        return self._planned_run(ws, key, rows, fn)
+
+    def _planned_run(self, ws, key, rows, fn):
         if not self.use_plans or self.probe is not None or ops._gemm_timing is not None or ops._plan_rec is not None:
             return fn()
         plans = ws.setdefault("plans", {})
@@ -776,7 +793,7 @@ class Engine:
         sv = self._saved
         if sv is None or sv["ticket"] != ticket:
             raise ops.ClgError("backward called for a forward whose activations were overwritten by a later forward")
-        with torch.no_grad():
+        with torch.no_grad(), ops.nvtx_range("clg.backward"):
             self._attach_grads()
             self._hot_valid = False          # new gradients: the block marks are stale until the next norm pass
             dl = dlogits.contiguous().float()
@@ -785,7 +802,8 @@ class Engine:
             else:
                 self._backward_uc2(dl, sv)
             if self.dp is not None:
-                self.dp.after_backward(self)
+                with ops.nvtx_range("clg.exchange"):
+                    self.dp.after_backward(self)
         self._saved = None
 
     def _wgrad(self, a, b, mod0, rows, cols, tokens=None):

@@ -4,6 +4,7 @@ torch's current CUDA stream and raise `ClgError` on any failure (no fallback).""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -13,6 +14,26 @@ from ._lib import (ACT_DGELU, ACT_DRELU, ACT_DTANH, ACT_GELU, ACT_GELU_GRAD, ACT
                    CLG_BF16, CLG_F32, GEMM_AUTO, GEMM_SIMT, GEMM_TC, ClgError)
 
 _launches = 0   # number of C-ABI kernel entry calls (bench.py reports it as gpu_launches)
+
+# CLG_NVTX=1: NVTX ranges around the phases of the step (forward, every encoder layer, head, backward, gradient exchange,
+# clip, AdamW) for Nsight Systems / `ncu --nvtx --nvtx-include`; off by default (a range costs ~1 us of host time)
+NVTX = os.environ.get("CLG_NVTX", "0") == "1"
+
+
+class nvtx_range:
+    __slots__ = ("name",)
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def launch_count() -> int:

@@ -239,13 +239,14 @@ class AdamW(Optimizer):
             # no norm pass marked the blocks of THIS gradient: the update is dense, and it makes m / v non-zero wherever the
             # gradient is - keep every block hot from here on, or a later clipped step would skip their moment decay
             eng._hot.fill_(1)
-        ops.adamw_step(eng.p_flat, eng.g_flat, fs["m"], fs["v"], fs["chunk_tensor"], tens,
-                       sumsq=eng._sumsq if max_norm is not None else None,
-                       max_norm=max_norm if max_norm is not None else 0.0, gscale=gscale,
-                       beta1=b1, beta2=b2, eps=g0["eps"], bias_c1=c1, bias_c2=c2,
-                       shadow=eng.shadow if eng.precision == "bf16" else None,
-                       mask_bits=eng.mask_bits if eng.has_masks else None,
-                       hot=eng._hot if eng._hot_valid else None, zero_grad=_FUSED_ZERO)
+        with ops.nvtx_range("clg.adamw"):
+            ops.adamw_step(eng.p_flat, eng.g_flat, fs["m"], fs["v"], fs["chunk_tensor"], tens,
+                           sumsq=eng._sumsq if max_norm is not None else None,
+                           max_norm=max_norm if max_norm is not None else 0.0, gscale=gscale,
+                           beta1=b1, beta2=b2, eps=g0["eps"], bias_c1=c1, bias_c2=c2,
+                           shadow=eng.shadow if eng.precision == "bf16" else None,
+                           mask_bits=eng.mask_bits if eng.has_masks else None,
+                           hot=eng._hot if eng._hot_valid else None, zero_grad=_FUSED_ZERO)
         eng._hot_valid = False
         eng.grads_zeroed = _FUSED_ZERO        # the step cleared the arena as it read it: the next backward skips its fill
         for p in self.state:

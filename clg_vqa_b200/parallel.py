@@ -273,8 +273,7 @@ def attach(model, optimizer=None, world_size: Optional[int] = None, group=None) 
         dist.broadcast(eng.p_flat, src=0, group=group)
         eng._shadow_versions = None
         # independent dropout masks per rank (the reference's processes have independent RNG streams)
-        rank = dist.get_rank(group)
-        eng.base_seed = (eng.base_seed ^ ((rank + 1) * 0x9E3779B97F4A7C15)) & 0x7FFFFFFFFFFFFFFF
+        eng.set_rank(dist.get_rank(group))
     ex.bind(eng)
     if ex.world > 1 and dev.type == "cuda":
         # leave a few SMs to NCCL: its kernels overlap the backward GEMMs, whose persistent CTAs (one per SM, static tile

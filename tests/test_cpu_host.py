@@ -257,3 +257,25 @@ def test_deferred_clip_is_applied_at_once_without_an_adamw_of_ours(monkeypatch):
         for p in params:
             optim._ENGINE_OF_PARAM.pop(id(p), None)
         optim._PENDING_CLIP.pop(id(eng), None)
+
+
+def test_dropout_seed_is_rank_salted_and_checkpoint_restores_the_rank_free_part():
+    """every data-parallel rank draws its own dropout masks (independent per-process RNG streams in the reference), also after
+    all ranks restored rank 0's checkpoint - whether resume() runs before parallel.attach (train_task.py:L280 vs L295) or after"""
+    cfg = C.uc2_base(1, vocab_size=32)
+    engines = []
+    for rank in range(2):
+        torch.manual_seed(77)
+        e = BertForVLTasks(cfg, C.gqa_task_cfg(), ["TASK15"]).engine
+        e.set_rank(rank)
+        engines.append(e)
+    assert engines[0].base_seed != engines[1].base_seed and engines[0].seed_root == engines[1].seed_root
+    engines[0].step_counter = 41
+    st = engines[0].rng_state()                      # what rank 0 writes
+    for e in engines:
+        e.set_rng_state(st)                          # resume after attach
+    assert engines[0].base_seed != engines[1].base_seed and engines[1].step_counter == 41
+    fresh = BertForVLTasks(cfg, C.gqa_task_cfg(), ["TASK15"]).engine
+    fresh.set_rng_state(st)                          # resume before attach
+    fresh.set_rank(1)
+    assert fresh.base_seed == engines[1].base_seed and fresh.step_seed() == engines[1].step_seed()

@@ -369,3 +369,22 @@ def test_launch_plans_replay_the_same_step(family):
             assert abs(l1 - l2) <= 1e-3 * abs(l2)
             assert abs(float(g1.norm()) - float(g2.norm())) <= 5e-2 * float(g2.norm())
     assert float((la - lb).abs().max()) <= 1e-2 * float(lb.abs().max())
+
+
+def test_nvtx_ranges_leave_the_step_unchanged(monkeypatch):
+    """CLG_NVTX=1 only brackets the phases of the step with NVTX ranges (forward, layers, backward, AdamW)"""
+    from clg_vqa_b200 import ops, optim
+    g, meta = _load_golden("uc2_L2_B4")
+    b = _batch(meta)
+    outs = []
+    for nvtx in (False, True):
+        monkeypatch.setattr(ops, "NVTX", nvtx)
+        model, cfg, task_cfg = _build_uc2(meta, "bf16")
+        opt = optim.AdamW(optim.grouped_parameters(model, 4e-5, 1e-4), lr=4e-5)
+        loss, _ = TU.ForwardModelsTrain(cfg, task_cfg, torch.device(DEV), "TASK15", S.batch_tuple(b), model)
+        loss.backward()
+        optim.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        with torch.no_grad():
+            outs.append((float(loss), _fwd(model, b).clone()))
+    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
