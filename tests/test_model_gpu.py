@@ -387,4 +387,5 @@ def test_nvtx_ranges_leave_the_step_unchanged(monkeypatch):
         opt.step()
         with torch.no_grad():
             outs.append((float(loss), _fwd(model, b).clone()))
-    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
+    assert outs[0][0] == outs[1][0]                       # same forward, bit for bit
+    assert _rel(outs[0][1], outs[1][1]) <= 1e-4           # after the step (the embedding backward's atomics reorder fp32 sums)
