@@ -338,7 +338,8 @@ typedef struct {
                                         the gradient it has just read is overwritten in place, which saves the separate
                                         fill pass over the arena; blocks that `hot` marks all-zero are not touched */
   void* shadow; const uint32_t* mask_bits;
-  const uint8_t* hot;                /* optional [n/256]: 0 = the block's g, m, v are all zero (marked by clg_sumsq on THIS
+  const uint8_t* hot;                /* optional [n/256], 8 B aligned (a chunk's 8 bytes are read as one word):
+                                        0 = the block's g, m, v are all zero (marked by clg_sumsq on THIS
                                         gradient): only the decoupled decay p -= lr*wd*p is applied - bit-identical to the
                                         dense update, 8 instead of 28 bytes of HBM traffic per parameter (the word-embedding
                                         rows a batch never touches); when lr*wd < 2^-25 that decay rounds to p itself and
