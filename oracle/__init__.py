@@ -16,8 +16,12 @@ Pinning status
     outputs of the reference itself are committed as fixtures under `tests/golden/` and
     `tests/test_oracle_golden.py` re-checks the oracle against them on every run.
     The reference ships no golden vectors or tests of its own for this path.
-  * adamw (optimiser / schedule): PARITY UNPINNED.  The algorithm lives in the un-vendored
-    pip dependency `pytorch-transformers>=1.1.0` (volta/requirements.txt:L51), which is absent
-    from /root/reference and not installed; it is restated from the published 1.x algorithm and
-    anchored on the reference's call sites (train_task.py:L263-276, L326-338) only.
+  * adamw (optimiser / schedule): PINNED (round 2).  The drivers import the optimiser from the un-vendored
+    pip dependency `pytorch-transformers>=1.1.0` (volta/requirements.txt:L51; call sites
+    train_task.py:L263-276, L326-338), but the reference tree carries that optimiser's step body verbatim
+    (features_extraction/mmf/mmf/modules/optimizers.py:L15-84).  `oracle/make_golden_adamw.py` executes it
+    unmodified on seeded parameters / gradients and commits the trajectories
+    (`tests/golden/adamw_ref_step.npz`); the oracle and `clg_vqa_b200.optim.AdamW` reproduce them bit for
+    bit on the CPU, the fused kernel within 2e-6 on the GPU.  The warm-up schedule is pinned against the
+    installed `transformers.get_linear_schedule_with_warmup` (the same lambda).
 """
